@@ -1,0 +1,180 @@
+/*
+ * vlmclip.h — C ABI of libvlmclip_b200.so, the sm_100a compute library behind the CLIP adapter
+ * fine-tuning hot path of Quillboltcode/VLM-CLIP.
+ *
+ * The reference has no FFI: its seam is the Python nn.Module API.  Each entry point below
+ * replaces the PyTorch eager ops the reference issues at the cited file:line; the Python mirror of the
+ * reference modules (vlm_clip_b200/*.py) binds them with ctypes.
+ *   HF = transformers/models/clip/modeling_clip.py (the third-party module holding the backbone arithmetic).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates on the hot path and
+ *     never synchronises the host.  Work is enqueued on the caller's stream (a CUstream / cudaStream_t
+ *     passed as void*).
+ *   - return value: 0 = ok, <0 = invalid argument (checked before launch), >0 = cudaError_t.
+ *     vlmclip_last_error() returns a thread-local message for the last non-zero return.
+ *   - matrices are row-major; "bf16" = __nv_bfloat16 storage; ld* = leading dimension in ELEMENTS.
+ *   - entry points are re-entrant (forward on the Python main thread, backward on autograd's thread).
+ */
+#ifndef VLMCLIP_H_
+#define VLMCLIP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLMCLIP_ABI_VERSION 1
+
+/* activation selector for GEMM epilogues and adapter kernels */
+enum {
+  VLMCLIP_ACT_NONE = 0,
+  VLMCLIP_ACT_QUICK_GELU = 1, /* x*sigmoid(1.702x), HF:349 (ACT2FN["quick_gelu"]) */
+  VLMCLIP_ACT_GELU_ERF = 2,   /* nn.GELU(), adapter/clip_adapter.py:12, adapter/peclip.py:11 */
+  VLMCLIP_ACT_RELU = 3        /* model_t.py:19, model_v.py:22 */
+};
+
+/* post-op selector of the fused bottleneck adapter */
+enum {
+  VLMCLIP_ADAPTER_RESIDUAL_LN = 0, /* LN(up(act(down x)) + x): adapter/clip_adapter.py:17-23,144-150 */
+  VLMCLIP_ADAPTER_RESIDUAL = 1,    /* up(act(down x)) + x: adapter/peclip.py:13-18 */
+  VLMCLIP_ADAPTER_BLEND_L2 = 2,    /* f = a*up(act(down x)) + (1-a)*x; f/|f|: model_t.py:163-169, model_v.py:280-286 */
+  VLMCLIP_ADAPTER_PLAIN = 3        /* up(act(down x)): model_t.py:21-22 */
+};
+
+int vlmclip_abi_version(void);
+const char* vlmclip_last_error(void);
+/* number of kernels launched by this library in the calling process since load (for bench.py gpu_launches) */
+int64_t vlmclip_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Dense layers.  C[M,N] = epilogue(A[M,K] * W[N,K]^T), tcgen05.mma + TMEM accumulators, TMA-fed.
+ * Replaces nn.Linear (aten::addmm) at HF:310-312,334 (q/k/v/out), HF:348-350 (fc1/fc2), HF:209 (patch conv as
+ * GEMM), HF:784-785 (projections).
+ *   epilogue, in order:  v = acc
+ *     if row_stats: v = rstd[m] * (v - mean[m] * col_c[n])      (LayerNorm folded into the layer; W holds
+ *                                                                gamma*W, col_c[n] = sum_k gamma[k] W[n,k],
+ *                                                                bias holds beta.W^T + b; HF:371,380)
+ *     if bias:      v += bias[n]
+ *     v = act(v)                                                 (HF:349)
+ *     if residual:  v += residual[m, n]                          (HF:377,382)
+ *   A, W, residual: bf16.  bias, col_c: fp32[N].  row_stats: fp32[M][2] = (mean, rstd).
+ *   C: bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1).  K % 8 == 0, N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0,
+ *   16-byte aligned base pointers.
+ * --------------------------------------------------------------------------------------------------------- */
+int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                      const float* bias, const void* residual, int64_t ldr, const float* row_stats,
+                      const float* col_c, int M, int N, int K, int act, int out_fp32, void* stream);
+
+/* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
+ *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */
+int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                           const float* beta, float* stats_out, int M, int D, float eps, void* stream);
+/* Row statistics only (mean, rstd) for the LN-folded GEMM epilogue. */
+int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, int D, float eps, void* stream);
+
+/* Patch extraction for the vision embedding (HF:209 Conv2d(k=stride=patch) as im2col + GEMM).
+ *   pixels: [B,3,H,W] fp32 (pix_bf16=0) or bf16 (pix_bf16=1), NCHW contiguous.
+ *   out: bf16 [B*(H/p)*(W/p), Kpad], Kpad = 3*p*p rounded up to a multiple of 64 (zero filled), column index
+ *   = c*p*p + i*p + j (matches patch_embedding.weight.view(D,-1), which the caller pads the same way). */
+int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* out, int B, int H, int W, int patch,
+                           void* stream);
+/* Assemble vision tokens and apply pre_layrnorm (HF:211-218, HF:677):
+ *   x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p]; y = LN(x).
+ *   patch: fp32 [B*(S-1), D] (the patch GEMM runs with out_fp32 = 1 so the position add happens in fp32 as in
+ *   the reference); cls fp32[D]; pos fp32[S,D]; y bf16 [B*S, D]. */
+int vlmclip_vision_embed_ln(const float* patch, const float* cls, const float* pos, const float* gamma,
+                            const float* beta, void* y, int B, int S, int D, float eps, void* stream);
+/* Text embeddings (HF:234-258): y[b,s] = tok[ids[b,s]] + pos[s].  ids int64 [B,S]; tok fp32[V,D]
+ * or bf16 (tok_bf16=1); pos fp32 [>=S, D]; y bf16 [B*S, D].  Out-of-range ids -> return -1 is NOT possible
+ * without a sync, so ids are clamped to [0,V) on device (the reference would raise IndexError). */
+int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y, int B,
+                       int S, int D, int V, void* stream);
+
+/* Multi-head self-attention core (HF:261-279,318-331): softmax(q k^T * scale + mask) v, fp32 softmax.
+ *   qkv: bf16 [B*S, 3*D] rows = tokens, columns = [q | k | v], head h at columns h*64..h*64+63 of each third.
+ *   out: bf16 [B*S, D].  head_dim fixed at 64 (all CLIP towers).  causal: 0/1 (HF:546-551).
+ *   key_mask (optional): uint8 [B,S], 1 = attend (attention_mask), applied to keys as in create_causal_mask.
+ *   A query row whose keys are all masked produces zeros. */
+int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
+                          float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused bottleneck adapter, fp32 (trainable weights live in fp32; adapter/clip_adapter.py:4-23,131-150,
+ * adapter/peclip.py:6-18, model_t.py:13-33, model_v.py:18-27).
+ *   h = act(x W1^T + b1);  u = h W2^T + b2;  y = post(u, x)     x,y: fp32 [R, D] (ldx); W1 [A,D]; W2 [D,A]
+ *   post: see VLMCLIP_ADAPTER_*; gamma/beta used by RESIDUAL_LN (eps), alpha by BLEND_L2.
+ *   x may be a strided view (ldx >= D), e.g. token 0 of every sequence (model_m.py:102,122).
+ *   x_bf16 = 1: x is bf16 (backbone activations), converted on load.
+ *   hmask (optional): fp32 [R, A] multiplier applied to h after the activation (the dropout mask of
+ *   model_v.py:24, already scaled by 1/(1-p); NULL in eval mode).
+ * Backward produces adapter-only gradients (the backbone is frozen: model_m.py:64-70); dx only if dx != NULL
+ * (full fine-tune).  Gradients are WRITTEN (not accumulated).  workspace: fp32, size from
+ * vlmclip_adapter_bwd_workspace(R, D, A) elements.
+ * --------------------------------------------------------------------------------------------------------- */
+int vlmclip_adapter_fwd(const void* x, int x_bf16, int64_t ldx, const float* W1, const float* b1,
+                        const float* W2, const float* b2, const float* gamma, const float* beta,
+                        const float* hmask, float* y, int R, int D, int A, int act, int post, float alpha,
+                        float eps, void* stream);
+int64_t vlmclip_adapter_bwd_workspace(int R, int D, int A);
+int vlmclip_adapter_bwd(const void* x, int x_bf16, int64_t ldx, const float* W1, const float* b1,
+                        const float* W2, const float* b2, const float* gamma, const float* beta,
+                        const float* hmask, const float* dy, float* dW1, float* db1, float* dW2, float* db2, float* dgamma,
+                        float* dbeta, float* dx, float* workspace, int R, int D, int A, int act, int post,
+                        float alpha, float eps, void* stream);
+
+/* Small fp32 linear for the projections (HF:784-785; model_m.py:103,123): y[R,N] = x[R,K] W[N,K]^T (+b),
+ * and its input gradient dx[R,K] = dy[R,N] W[N,K].  fp32 SIMT (K,N <= 1024-ish, R = batch). */
+int vlmclip_linear_f32(const float* x, int64_t ldx, const float* W, const float* b, float* y, int R, int N,
+                       int K, void* stream);
+int vlmclip_linear_f32_dgrad(const float* dy, const float* W, float* dx, int R, int N, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Contrastive head (model_m.py:146-171): L2-normalise, exp(logit_scale) * T I^T, symmetric cross-entropy,
+ * and its gradient w.r.t. the UN-normalised features.
+ *   txt, img: fp32 [N, P] un-normalised features of the GLOBAL batch (after all-gather under DP).
+ *   row0, nloc: this rank's rows [row0, row0+nloc) — gradients are produced for these rows only, including
+ *               both the row-softmax and the column-softmax terms (exact dL_global/d(local features)).
+ *   outputs: txt_n, img_n fp32 [N,P] normalised; logits_per_text fp32 [N,N] (optional, may be NULL);
+ *            loss fp32[1]; d_txt, d_img fp32 [nloc, P] (optional); d_logit_scale fp32[1] (optional; gradient
+ *            w.r.t. the log-scale parameter, local rows' share).
+ *   workspace fp32: vlmclip_clip_loss_workspace(N, P) elements.
+ * --------------------------------------------------------------------------------------------------------- */
+int64_t vlmclip_clip_loss_workspace(int N, int P);
+int vlmclip_clip_loss(const float* txt, const float* img, float logit_scale_exp, float* txt_n, float* img_n,
+                      float* logits_per_text, float* loss, float* d_txt, float* d_img, float* d_logit_scale,
+                      float* workspace, int N, int P, int row0, int nloc, void* stream);
+
+/* Class-prompt head (model_t.py:184-187,213-242; model_v.py:340-343): logits[B,C] = scale * f_img f_txt^T,
+ * cross-entropy against int64 labels (hard) or fp32 [B,C] probabilities (soft), mean reduction, plus
+ * gradients w.r.t. f_img, f_txt.  probs (optional) = softmax(logits).  group > 1: logits are first
+ * max-reduced over `group` consecutive prompts per class (predict_with_all_descriptions, model_t.py:264-298;
+ * forward only; f_txt is then [C*group, P]).  workspace: fp32 B*C + B elements, needed when loss or
+ * gradients are requested. */
+int vlmclip_class_head(const float* f_img, const float* f_txt, float scale, const int64_t* labels,
+                       const float* soft_labels, float* logits, float* probs, float* loss, float* d_img,
+                       float* d_txt, float* workspace, int B, int C, int P, int group, void* stream);
+
+/* L2 normalise rows: y = x / |x| (model_t.py:160). */
+int vlmclip_l2norm_rows(const float* x, float* y, int R, int P, void* stream);
+int vlmclip_l2norm_rows_bwd(const float* x, const float* dy, float* dx, int R, int P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser tail (trainer.py:91-99): global grad-norm, clip to max_norm, AdamW (decoupled weight decay),
+ * one launch over a flat fp32 parameter arena, no host sync.  step_size/bias corrections are computed on
+ * device from `step` (int32[1], incremented by the kernel).  lr is read from lr_dev (fp32[1]) so a host
+ * scheduler can update it asynchronously.  grad_norm_out fp32[1] receives the pre-clip norm.
+ * --------------------------------------------------------------------------------------------------------- */
+int vlmclip_adamw_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                            float max_norm, int32_t* step, float* grad_norm_out, float* workspace,
+                            void* stream);
+
+/* bf16 <-> fp32 casts with optional row gather (token-0 slice): y[r, :] = x[r*ldx : r*ldx + D] */
+int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLMCLIP_H_ */

@@ -1,0 +1,355 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against a plain fp32 PyTorch statement of the same
+op (the oracle's primitives where they exist).  Tolerances are written next to each check; bf16 tensor-core
+paths are compared after rounding the inputs to bf16 so only accumulation order / output rounding differ."""
+import math
+
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+GEMM_CASES = [
+    # M, N, K, bias, act, residual, rowstats, out_fp32
+    (128, 256, 64, False, 0, False, False, False),
+    (128, 128, 128, True, 0, False, False, False),
+    (256, 512, 768, True, 0, False, False, False),
+    (1000, 768, 768, True, 0, True, False, False),      # M tail, residual (out-proj / fc2)
+    (394, 3072, 768, True, 1, False, False, False),     # fc1 + quick_gelu
+    (300, 2304, 768, True, 0, False, True, False),      # LN-folded QKV
+    (640, 264, 512, True, 0, False, False, False),      # N tail inside a 256-wide tile
+    (130, 72, 64, True, 3, False, False, False),        # small N (128-wide tile), relu
+    (392, 768, 640, False, 0, False, False, True),      # patch embed: fp32 out, no bias
+    (2048, 512, 2048, True, 0, True, False, False),     # text fc2
+    (4096, 1024, 4096, True, 0, True, False, False),    # L/14 fc2: long K loop, many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("M,N,K,has_bias,act,has_res,has_stats,out_fp32", GEMM_CASES)
+def test_gemm(cuda, M, N, K, has_bias, act, has_res, has_stats, out_fp32):
+    from vlm_clip_b200 import ops
+
+    g = _gen(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=cuda, generator=g).to(bf16)
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(bf16)
+    bias = torch.randn(N, device=cuda, generator=g) if has_bias else None
+    res = torch.randn(M, N, device=cuda, generator=g).to(bf16) if has_res else None
+    stats = colc = None
+    ref = a.float() @ w.float().t()
+    if has_stats:
+        stats = torch.stack([torch.randn(M, device=cuda, generator=g) * 0.1,
+                             torch.rand(M, device=cuda, generator=g) + 0.5], dim=1).contiguous()
+        colc = torch.randn(N, device=cuda, generator=g)
+        ref = stats[:, 1:2] * (ref - stats[:, 0:1] * colc[None])
+    if has_bias:
+        ref = ref + bias
+    if act == 1:
+        ref = O.quick_gelu(ref)
+    elif act == 3:
+        ref = torch.relu(ref)
+    if has_res:
+        ref = ref + res.float()
+    out = ops.gemm(a, w, bias=bias, residual=res, act=act, out_fp32=out_fp32, row_stats=stats, col_c=colc)
+    torch.cuda.synchronize()
+    assert out.dtype == (f32 if out_fp32 else bf16)
+    # fp32 accumulation of exact bf16 products: error is output rounding (2^-9 relative per element for bf16)
+    tol = 2e-5 if out_fp32 else 4e-3
+    assert _rel(out, ref) < tol, f"rel err {_rel(out, ref)}"
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_rejects_bad_args(cuda):
+    from vlm_clip_b200 import ops
+
+    a = torch.zeros(16, 60, device=cuda, dtype=bf16)  # K not a multiple of 8
+    w = torch.zeros(16, 60, device=cuda, dtype=bf16)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)
+
+
+@pytest.mark.parametrize("M,D", [(8, 512), (197, 768), (1001, 1024), (33, 2048)])
+def test_layernorm_and_stats(cuda, M, D):
+    from vlm_clip_b200 import ops
+
+    g = _gen(M + D)
+    x = (torch.randn(M, D, device=cuda, generator=g) * 2 + 0.5).to(bf16)
+    gamma = torch.randn(D, device=cuda, generator=g)
+    beta = torch.randn(D, device=cuda, generator=g)
+    stats = torch.empty(M, 2, device=cuda)
+    y = ops.layernorm(x, gamma, beta, 1e-5, stats=stats)
+    ref = O.layer_norm(x.float(), gamma, beta)
+    assert _rel(y, ref) < 4e-3
+    mu = x.float().mean(-1)
+    rstd = 1 / torch.sqrt(x.float().var(-1, unbiased=False) + 1e-5)
+    assert torch.allclose(stats[:, 0], mu, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], rstd, atol=1e-5, rtol=1e-4)
+    s2 = ops.row_stats(x, 1e-5)
+    assert torch.equal(s2, stats)
+
+
+@pytest.mark.parametrize("patch,dt", [(32, f32), (16, f32), (14, f32), (16, bf16)])
+def test_im2col_and_embed(cuda, patch, dt):
+    from vlm_clip_b200 import ops
+
+    g = _gen(patch)
+    B, D = 3, 256
+    pix = torch.randn(B, 3, 224, 224, device=cuda, generator=g).to(dt)
+    cols = ops.im2col(pix, patch)
+    K = 3 * patch * patch
+    ref = torch.nn.functional.unfold(pix.float(), kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, K)
+    assert torch.equal(cols[:, :K].float(), ref.to(bf16).float())  # pure data movement + rounding: bit exact
+    assert (cols[:, K:] == 0).all()
+    S = (224 // patch) ** 2 + 1
+    patch_out = torch.randn(B * (S - 1), D, device=cuda, generator=g)
+    cls = torch.randn(D, device=cuda, generator=g)
+    pos = torch.randn(S, D, device=cuda, generator=g)
+    gamma = torch.randn(D, device=cuda, generator=g)
+    beta = torch.randn(D, device=cuda, generator=g)
+    y = ops.vision_embed_ln(patch_out, cls, pos, gamma, beta, B, S)
+    x = torch.cat([cls.expand(B, 1, D), patch_out.view(B, S - 1, D)], 1) + pos[None]
+    assert _rel(y.view(B, S, D), O.layer_norm(x, gamma, beta)) < 4e-3
+
+
+def test_text_embed(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(5)
+    V, D, B, S = 1000, 512, 4, 77
+    tok = torch.randn(V, D, device=cuda, generator=g)
+    pos = torch.randn(77, D, device=cuda, generator=g)
+    ids = torch.randint(0, V, (B, S), device=cuda, generator=g)
+    y = ops.text_embed(ids, tok, pos)
+    ref = (tok[ids] + pos[None]).to(bf16).view(B * S, D)
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("B,S,H,causal,masked", [(2, 50, 12, False, False), (3, 197, 12, False, False),
+                                                 (2, 257, 16, False, False), (4, 77, 8, True, False),
+                                                 (4, 77, 8, True, True), (1, 16, 1, True, False),
+                                                 (2, 64, 2, False, True)])
+def test_attention(cuda, B, S, H, causal, masked):
+    from vlm_clip_b200 import ops
+
+    g = _gen(B * 1000 + S)
+    D = H * 64
+    qkv = torch.randn(B * S, 3 * D, device=cuda, generator=g).to(bf16)
+    key_mask = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), device=cuda, generator=g)
+        key_mask = (torch.arange(S, device=cuda)[None] < lens[:, None]).to(torch.uint8).contiguous()
+    out = ops.attention(qkv, B, S, H, causal=causal, key_mask=key_mask)
+    q, k, v = qkv.float().view(B, S, 3, D).unbind(2)
+    ref = O.attention_core(q, k, v, H, causal, key_mask).reshape(B * S, D)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    # probabilities are rounded to bf16 before P.V (2^-9) and the output is bf16
+    assert _rel(out, ref) < 8e-3, f"rel err {_rel(out, ref)}"
+
+
+ADAPTER_CASES = [
+    # R, D, A, act, post
+    (8, 512, 256, "gelu", 0), (256, 768, 256, "gelu", 0), (5, 1024, 256, "gelu", 1),
+    (26, 512, 64, "relu", 2), (8, 768, 192, "relu", 2), (7, 512, 64, "relu", 3),
+]
+
+
+def _adapter_ref(x, W1, b1, W2, b2, gamma, beta, act, post, alpha):
+    u = O.bottleneck(x, W1, b1, W2, b2, act)
+    if post == 0:
+        return O.layer_norm(u + x, gamma, beta)
+    if post == 1:
+        return u + x
+    if post == 2:
+        f = alpha * u + (1 - alpha) * x
+        return f / f.norm(dim=-1, keepdim=True)
+    return u
+
+
+@pytest.mark.parametrize("R,D,A,act,post", ADAPTER_CASES)
+def test_adapter_fwd_bwd(cuda, R, D, A, act, post):
+    from vlm_clip_b200 import ops, _native as N
+
+    g = _gen(R + D + A + post)
+    x = torch.randn(R, D, device=cuda, generator=g)
+    W1 = (torch.rand(A, D, device=cuda, generator=g) * 2 - 1) / math.sqrt(D)
+    b1 = (torch.rand(A, device=cuda, generator=g) * 2 - 1) / math.sqrt(D)
+    W2 = (torch.rand(D, A, device=cuda, generator=g) * 2 - 1) / math.sqrt(A)
+    b2 = (torch.rand(D, device=cuda, generator=g) * 2 - 1) / math.sqrt(A)
+    gamma = torch.rand(D, device=cuda, generator=g) + 0.5
+    beta = torch.randn(D, device=cuda, generator=g) * 0.1
+    dy = torch.randn(R, D, device=cuda, generator=g)
+    alpha = 0.2
+    params = [t.clone().requires_grad_(True) for t in (x, W1, b1, W2, b2, gamma, beta)]
+    ref = _adapter_ref(*params, act, post, alpha)
+    ref.backward(dy)
+    mine = [t.clone().requires_grad_(True) for t in (x, W1, b1, W2, b2, gamma, beta)]
+    y = ops.adapter(mine[0], *mine[1:5], mine[5] if post == 0 else None, mine[6] if post == 0 else None,
+                    act=N.ACT_GELU_ERF if act == "gelu" else N.ACT_RELU, post=post, alpha=alpha)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    assert torch.allclose(y, ref, atol=2e-5, rtol=2e-5), (y - ref).abs().max()
+    names = ["x", "W1", "b1", "W2", "b2", "gamma", "beta"]
+    for n, p, q in zip(names, mine, params):
+        if q.grad is None:
+            continue
+        assert p.grad is not None, n
+        err = (p.grad - q.grad).abs().max().item()
+        scale = q.grad.abs().max().item() + 1e-12
+        assert err <= 2e-4 * scale + 1e-6, f"grad {n}: {err} vs scale {scale}"
+
+
+def test_adapter_strided_bf16_token0(cuda):
+    """The hot-path call: x = token 0 of every sequence of a bf16 [B*S, D] activation (model_m.py:102,122)."""
+    from vlm_clip_b200 import ops, _native as N
+
+    g = _gen(77)
+    B, S, D, A = 6, 50, 768, 256
+    act = torch.randn(B * S, D, device=cuda, generator=g).to(bf16)
+    W1 = torch.randn(A, D, device=cuda, generator=g) * 0.03
+    b1 = torch.zeros(A, device=cuda)
+    W2 = torch.randn(D, A, device=cuda, generator=g) * 0.05
+    b2 = torch.zeros(D, device=cuda)
+    gamma, beta = torch.ones(D, device=cuda), torch.zeros(D, device=cuda)
+    y = ops.adapter(act, W1, b1, W2, b2, gamma, beta, act=N.ACT_GELU_ERF, post=0, ldx=S * D, rows=B)
+    x0 = act.view(B, S, D)[:, 0].float()
+    ref = _adapter_ref(x0, W1, b1, W2, b2, gamma, beta, "gelu", 0, 0.0)
+    assert torch.allclose(y, ref, atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.parametrize("Nn,P,scale", [(8, 512, 14.285), (256, 512, 14.285), (256, 512, 100.0), (100, 768, 100.0),
+                                        (1, 512, 14.285)])
+def test_clip_loss(cuda, Nn, P, scale):
+    from vlm_clip_b200 import ops
+
+    g = _gen(Nn + P)
+    t = torch.randn(Nn, P, device=cuda, generator=g).requires_grad_(True)
+    i = torch.randn(Nn, P, device=cuda, generator=g).requires_grad_(True)
+    ref = O.contrastive_loss(t, i, torch.tensor(math.log(scale), device=cuda))
+    ref["loss"].backward()
+    t2 = t.detach().clone().requires_grad_(True)
+    i2 = i.detach().clone().requires_grad_(True)
+    loss, tn, in_, logits = ops.clip_loss(t2, i2, scale)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref["loss"].item()) < 1e-4  # north_star: fp32 loss within 1e-4
+    assert torch.allclose(tn, ref["text_features"], atol=1e-6)
+    assert torch.allclose(in_, ref["image_features"], atol=1e-6)
+    assert torch.allclose(logits, ref["logits_per_text"], atol=2e-4, rtol=1e-5)
+    for a, b in ((t2.grad, t.grad), (i2.grad, i.grad)):
+        assert (a - b).abs().max().item() <= 2e-4 * (b.abs().max().item() + 1e-12) + 1e-7
+
+
+def test_clip_loss_data_parallel_rows(cuda):
+    """R emulated ranks, each differentiating only its own rows of the global loss, reproduce the single-process
+    gradient exactly."""
+    from vlm_clip_b200 import ops
+
+    g = _gen(11)
+    Nn, P, R = 64, 512, 4
+    t = torch.randn(Nn, P, device=cuda, generator=g)
+    i = torch.randn(Nn, P, device=cuda, generator=g)
+    tf, if_ = t.clone().requires_grad_(True), i.clone().requires_grad_(True)
+    full, *_ = ops.clip_loss(tf, if_, 14.285)
+    full.backward()
+    nl = Nn // R
+    for r in range(R):
+        tl = t[r * nl:(r + 1) * nl].clone().requires_grad_(True)
+        il = i[r * nl:(r + 1) * nl].clone().requires_grad_(True)
+        loss, *_ = ops.clip_loss(tl, il, 14.285, txt_all=t, img_all=i, row0=r * nl, want_logits=False)
+        loss.backward()
+        assert abs(loss.item() - full.item()) < 1e-6
+        assert torch.allclose(tl.grad, tf.grad[r * nl:(r + 1) * nl], atol=1e-7, rtol=1e-5)
+        assert torch.allclose(il.grad, if_.grad[r * nl:(r + 1) * nl], atol=1e-7, rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,P,soft", [(8, 26, 512, False), (8, 26, 512, True), (32, 7, 768, False)])
+def test_class_head(cuda, B, C, P, soft):
+    from vlm_clip_b200 import ops
+
+    g = _gen(B + C)
+    fi = torch.nn.functional.normalize(torch.randn(B, P, device=cuda, generator=g), dim=-1)
+    ft = torch.nn.functional.normalize(torch.randn(C, P, device=cuda, generator=g), dim=-1)
+    if soft:
+        hot = (torch.rand(B, C, device=cuda, generator=g) < 0.1).float()
+        hot[torch.arange(B), torch.randint(0, C, (B,), device=cuda, generator=g)] = 1.0
+        lab = hot / hot.sum(1, keepdim=True)
+    else:
+        lab = torch.randint(0, C, (B,), device=cuda, generator=g)
+    a, b = fi.clone().requires_grad_(True), ft.clone().requires_grad_(True)
+    ref_logits = 14.285 * a @ b.t()
+    ref = O.class_prompt_loss(ref_logits, lab)
+    ref.backward()
+    a2, b2 = fi.clone().requires_grad_(True), ft.clone().requires_grad_(True)
+    loss, logits = ops.class_head_loss(a2, b2, 14.285, labels=None if soft else lab, soft_labels=lab if soft else None)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert torch.allclose(logits, ref_logits, atol=1e-4)
+    assert torch.allclose(a2.grad, a.grad, atol=1e-6, rtol=1e-4)
+    assert torch.allclose(b2.grad, b.grad, atol=1e-6, rtol=1e-4)
+    probs, _ = ops.class_head_probs(fi, ft, 100.0)
+    assert torch.allclose(probs, torch.softmax(100.0 * fi @ ft.t(), 1), atol=1e-5)
+    assert torch.equal(probs.argmax(1), (100.0 * fi @ ft.t()).argmax(1))
+
+
+def test_class_head_group_max(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(3)
+    B, C, G, P = 16, 7, 5, 512
+    fi = torch.nn.functional.normalize(torch.randn(B, P, device=cuda, generator=g), dim=-1)
+    ft = torch.nn.functional.normalize(torch.randn(C * G, P, device=cuda, generator=g), dim=-1)
+    probs, _ = ops.class_head_probs(fi, ft, 100.0, group=G)
+    ref = torch.softmax((100.0 * fi @ ft.t()).view(B, C, G).max(-1).values, 1)
+    assert torch.allclose(probs, ref, atol=1e-5)
+
+
+def test_l2norm_and_linear(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(9)
+    x = torch.randn(37, 512, device=cuda, generator=g)
+    W = torch.randn(300, 512, device=cuda, generator=g) * 0.05
+    a = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.normalize(a @ W.t(), dim=-1)
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    b = x.clone().requires_grad_(True)
+    out = ops.l2norm(ops.linear_f32(b, W))
+    out.backward(dy)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(b.grad, a.grad, atol=1e-5, rtol=1e-4)
+
+
+def test_fused_adamw_matches_torch(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(21)
+    shapes = [(256, 768), (256,), (768, 256), (768,), (768,), (768,)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device=cuda, generator=g) * 0.05) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref_opt = torch.optim.AdamW(qs, lr=5e-5, weight_decay=0.01)
+    opt = ops.FusedAdamW(ps, lr=5e-5, weight_decay=0.01, max_grad_norm=1.0)
+    for it in range(3):
+        grads = [torch.randn(*s, device=cuda, generator=g) * (3.0 if it == 0 else 0.01) for s in shapes]
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        for p, q, gr in zip(ps, qs, grads):
+            p.grad.copy_(gr)
+            q.grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(qs, 1.0)
+        ref_opt.step()
+        opt.step()
+        assert abs(opt.grad_norm.item() - norm.item()) < 1e-4 * max(1.0, norm.item())
+        for p, q in zip(ps, qs):
+            assert torch.allclose(p, q, atol=1e-7, rtol=1e-5)

@@ -1,0 +1,321 @@
+// Row-wise, HBM-bound kernels of the towers: LayerNorm, row statistics, patch extraction, token
+// assembly.  One warp per row, 16-byte vector accesses, fp32 statistics (two-pass in registers).
+// References: HF modeling_clip.py:371,380,562,677 (LayerNorm), :202-218 (vision embeddings),
+// :234-258 (text embeddings).
+#include "../../include/vlmclip.h"
+#include "common.cuh"
+
+namespace vlmclip {
+void count_launch(int n);
+
+namespace {
+
+constexpr int ROWS_PER_BLOCK = 8;
+constexpr int MAX_VEC = 8;  // 8 x (32 lanes x 8 elements) = D <= 2048
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  f[0] = bf16_lo(q.x);
+  f[1] = bf16_hi(q.x);
+  f[2] = bf16_lo(q.y);
+  f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z);
+  f[5] = bf16_hi(q.z);
+  f[6] = bf16_lo(q.w);
+  f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// mean / rstd of one row held as v[nv][8] per lane
+__device__ __forceinline__ void row_mean_rstd(float (*v)[8], int nvec_lane_valid[MAX_VEC], int D, float eps,
+                                              float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (nvec_lane_valid[i])
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+  s = warp_sum(s);
+  mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i)
+    if (nvec_lane_valid[i])
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+  q = warp_sum(q);
+  rstd = rsqrtf(q / (float)D + eps);
+}
+
+// MODE 0: y = LN(x) (+stats)   MODE 1: stats only
+template <int MODE>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ stats, int M,
+                 int D, float eps) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  float v[MAX_VEC][8];
+  int valid[MAX_VEC];
+  const __nv_bfloat16* xr = x + (int64_t)row * ldx;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int vi = lane + i * 32;
+    valid[i] = vi < nvec;
+    if (valid[i]) {
+      const uint4 q = ld_nc_v4(xr + vi * 8);
+      unpack8(q, v[i]);
+    }
+  }
+  float mean, rstd;
+  row_mean_rstd(v, valid, D, eps, mean, rstd);
+  if (stats != nullptr && lane == 0) {
+    stats[2 * (int64_t)row] = mean;
+    stats[2 * (int64_t)row + 1] = rstd;
+  }
+  if (MODE == 0) {
+    __nv_bfloat16* yr = y + (int64_t)row * ldy;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+      if (valid[i]) {
+        const int c = (lane + i * 32) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+        st_v4(yr + c, pack8(o));
+      }
+    }
+  }
+}
+
+// out[m, k] = pixel[b, c, py*p + i, px*p + j],  m = (b, py, px), k = c*p*p + i*p + j; k >= 3*p*p -> 0
+template <typename PixT>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const PixT* __restrict__ pix, __nv_bfloat16* __restrict__ out, int B, int H, int W, int p, int Kpad) {
+  const int gw = W / p, gh = H / p;
+  const int kvec = Kpad >> 3;
+  const int64_t total = (int64_t)B * gh * gw * kvec;
+  const int pp = p * p;
+  const int K = 3 * pp;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int kv = (int)(idx % kvec);
+    const int64_t m = idx / kvec;
+    const int px = (int)(m % gw);
+    const int py = (int)((m / gw) % gh);
+    const int b = (int)(m / ((int64_t)gw * gh));
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kv * 8 + e;
+      if (k < K) {
+        const int c = k / pp;
+        const int r = k - c * pp;
+        const int i = r / p;
+        const int j = r - i * p;
+        f[e] = (float)pix[(((int64_t)b * 3 + c) * H + (py * p + i)) * W + (px * p + j)];
+      } else {
+        f[e] = 0.f;
+      }
+    }
+    st_v4(out + m * Kpad + kv * 8, pack8(f));
+  }
+}
+
+// vision tokens: x[b,0] = cls + pos[0]; x[b,1+q] = patch[b,q] + pos[1+q]; y = LN(x)
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                       const float* __restrict__ pos, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int B, int S, int D,
+                       float eps) {
+  const int64_t row = blockIdx.x * (int64_t)ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * S) return;
+  const int lane = threadIdx.x & 31;
+  const int s = (int)(row % S);
+  const int64_t b = row / S;
+  const int nvec = D >> 3;
+  const float* src = (s == 0) ? cls : patch + (b * (S - 1) + (s - 1)) * (int64_t)D;
+  const float* pr = pos + (int64_t)s * D;
+  float v[MAX_VEC][8];
+  int valid[MAX_VEC];
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int vi = lane + i * 32;
+    valid[i] = vi < nvec;
+    if (valid[i]) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + vi * 8));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + vi * 8 + 4));
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pr + vi * 8));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pr + vi * 8 + 4));
+      v[i][0] = a0.x + p0.x;
+      v[i][1] = a0.y + p0.y;
+      v[i][2] = a0.z + p0.z;
+      v[i][3] = a0.w + p0.w;
+      v[i][4] = a1.x + p1.x;
+      v[i][5] = a1.y + p1.y;
+      v[i][6] = a1.z + p1.z;
+      v[i][7] = a1.w + p1.w;
+    }
+  }
+  float mean, rstd;
+  row_mean_rstd(v, valid, D, eps, mean, rstd);
+  __nv_bfloat16* yr = y + row * D;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (valid[i]) {
+      const int c = (lane + i * 32) * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, __ldg(gamma + c + j), __ldg(beta + c + j));
+      st_v4(yr + c, pack8(o));
+    }
+  }
+}
+
+template <typename TokT>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+text_embed_kernel(const int64_t* __restrict__ ids, const TokT* __restrict__ tok, const float* __restrict__ pos,
+                  __nv_bfloat16* __restrict__ y, int B, int S, int D, int V) {
+  const int64_t row = blockIdx.x * (int64_t)ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * S) return;
+  const int lane = threadIdx.x & 31;
+  const int s = (int)(row % S);
+  int64_t id = ids[row];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const TokT* tr = tok + id * D;
+  const float* pr = pos + (int64_t)s * D;
+  for (int c = lane * 8; c < D; c += 256) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (float)tr[c + j] + __ldg(pr + c + j);
+    st_v4(y + row * D + c, pack8(o));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ y, int R, int D) {
+  const int64_t total = (int64_t)R * D;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / D;
+    const int c = (int)(idx - r * D);
+    y[idx] = __bfloat162float(x[r * ldx + c]);
+  }
+}
+
+int grid_for(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+}  // namespace vlmclip
+
+using namespace vlmclip;
+
+extern "C" int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                                      const float* beta, float* stats_out, int M, int D, float eps, void* stream) {
+  VLMCLIP_CHECK_ARG(x && y && gamma && beta, "layernorm: null pointer");
+  VLMCLIP_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && D <= MAX_VEC * 256, "layernorm: D=%d must be a multiple of 8, <= %d",
+                    D, MAX_VEC * 256);
+  VLMCLIP_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= D && ldy >= D, "layernorm: bad leading dimension");
+  VLMCLIP_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 &&
+                        (uintptr_t)beta % 16 == 0,
+                    "layernorm: pointers must be 16-byte aligned");
+  const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  count_launch(1);
+  layernorm_kernel<0><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, gamma, beta, stats_out, M, D, eps);
+  return report_cuda(cudaGetLastError(), "layernorm_kernel launch");
+}
+
+extern "C" int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, int D, float eps,
+                                      void* stream) {
+  VLMCLIP_CHECK_ARG(x && stats_out, "row_stats: null pointer");
+  VLMCLIP_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && D <= MAX_VEC * 256, "row_stats: D=%d must be a multiple of 8, <= %d",
+                    D, MAX_VEC * 256);
+  VLMCLIP_CHECK_ARG(ldx % 8 == 0 && ldx >= D && (uintptr_t)x % 16 == 0, "row_stats: bad ldx/alignment");
+  const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  count_launch(1);
+  layernorm_kernel<1><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, stats_out, M, D, eps);
+  return report_cuda(cudaGetLastError(), "row_stats kernel launch");
+}
+
+extern "C" int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* out, int B, int H, int W, int patch,
+                                      void* stream) {
+  VLMCLIP_CHECK_ARG(pixels && out, "im2col: null pointer");
+  VLMCLIP_CHECK_ARG(B > 0 && patch > 0 && H % patch == 0 && W % patch == 0, "im2col: H=%d W=%d not divisible by patch=%d",
+                    H, W, patch);
+  const int K = 3 * patch * patch;
+  const int Kpad = (K + 63) / 64 * 64;
+  VLMCLIP_CHECK_ARG((uintptr_t)out % 16 == 0, "im2col: out must be 16-byte aligned");
+  const int64_t total = (int64_t)B * (H / patch) * (W / patch) * (Kpad / 8);
+  count_launch(1);
+  if (pix_bf16)
+    im2col_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)pixels, (__nv_bfloat16*)out, B, H, W, patch, Kpad);
+  else
+    im2col_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)pixels,
+                                                                                 (__nv_bfloat16*)out, B, H, W,
+                                                                                 patch, Kpad);
+  return report_cuda(cudaGetLastError(), "im2col_kernel launch");
+}
+
+extern "C" int vlmclip_vision_embed_ln(const float* patch, const float* cls, const float* pos, const float* gamma,
+                                       const float* beta, void* y, int B, int S, int D, float eps, void* stream) {
+  VLMCLIP_CHECK_ARG(patch && cls && pos && gamma && beta && y, "vision_embed_ln: null pointer");
+  VLMCLIP_CHECK_ARG(B > 0 && S > 1 && D % 8 == 0 && D <= MAX_VEC * 256, "vision_embed_ln: bad dims B=%d S=%d D=%d", B, S, D);
+  VLMCLIP_CHECK_ARG((uintptr_t)patch % 16 == 0 && (uintptr_t)cls % 16 == 0 && (uintptr_t)pos % 16 == 0 &&
+                        (uintptr_t)y % 16 == 0,
+                    "vision_embed_ln: pointers must be 16-byte aligned");
+  const int64_t rows = (int64_t)B * S;
+  const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  count_launch(1);
+  vision_embed_ln_kernel<<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+      patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps);
+  return report_cuda(cudaGetLastError(), "vision_embed_ln_kernel launch");
+}
+
+extern "C" int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y,
+                                  int B, int S, int D, int V, void* stream) {
+  VLMCLIP_CHECK_ARG(ids && tok && pos && y, "text_embed: null pointer");
+  VLMCLIP_CHECK_ARG(B > 0 && S > 0 && D % 8 == 0 && V > 0, "text_embed: bad dims");
+  VLMCLIP_CHECK_ARG((uintptr_t)y % 16 == 0, "text_embed: y must be 16-byte aligned");
+  const int64_t rows = (int64_t)B * S;
+  const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  count_launch(1);
+  if (tok_bf16)
+    text_embed_kernel<__nv_bfloat16><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+        ids, (const __nv_bfloat16*)tok, pos, (__nv_bfloat16*)y, B, S, D, V);
+  else
+    text_embed_kernel<float><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+        ids, (const float*)tok, pos, (__nv_bfloat16*)y, B, S, D, V);
+  return report_cuda(cudaGetLastError(), "text_embed_kernel launch");
+}
+
+extern "C" int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream) {
+  VLMCLIP_CHECK_ARG(x && y && R > 0 && D > 0 && ldx >= D, "gather_rows: bad arguments");
+  count_launch(1);
+  gather_rows_kernel<<<grid_for((int64_t)R * D, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx,
+                                                                                    y, R, D);
+  return report_cuda(cudaGetLastError(), "gather_rows_kernel launch");
+}

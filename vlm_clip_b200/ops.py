@@ -1,0 +1,412 @@
+"""Tensor-level wrappers over the C ABI (include/vlmclip.h) plus the autograd glue of the trainable path.
+
+Everything here runs on CUDA through libvlmclip_b200.so.  torch is used to allocate outputs and workspaces
+and to carry autograd edges; no torch operator does arithmetic on the hot path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as N
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _req(cond: bool, msg: str) -> None:
+    if not cond:
+        raise ValueError(msg)
+
+
+# --------------------------------------------------------------------------------------------- dense layers
+def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=False, row_stats=None, col_c=None):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores (vlmclip_gemm_bf16)."""
+    _req(a.dtype == bf16 and w.dtype == bf16, "gemm: a and w must be bf16")
+    _req(a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], "gemm: shape mismatch")
+    _req(a.stride(1) == 1 and w.stride(1) == 1, "gemm: operands must be row-major (K contiguous)")
+    M, K = a.shape
+    Nn = w.shape[0]
+    if out is None:
+        out = torch.empty((M, Nn), device=a.device, dtype=f32 if out_fp32 else bf16)
+    _req(out.stride(1) == 1 and out.shape == (M, Nn), "gemm: bad out")
+    _req(out.dtype == (f32 if out_fp32 else bf16), "gemm: out dtype")
+    if residual is not None:
+        _req(residual.dtype == bf16 and residual.shape == (M, Nn) and residual.stride(1) == 1, "gemm: bad residual")
+    lib = N.load()
+    N.check(
+        lib.vlmclip_gemm_bf16(
+            N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(out), out.stride(0), N.ptr(bias), N.ptr(residual),
+            residual.stride(0) if residual is not None else 0, N.ptr(row_stats), N.ptr(col_c), M, Nn, K, int(act),
+            1 if out_fp32 else 0, N.stream()),
+        "vlmclip_gemm_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
+    _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm: x must be bf16 [M, D]")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_layernorm_bf16(N.ptr(x), x.stride(0), N.ptr(out), out.stride(0), N.ptr(gamma), N.ptr(beta),
+                                        N.ptr(stats), M, D, float(eps), N.stream()), "vlmclip_layernorm_bf16")
+    return out
+
+
+def row_stats(x, eps=1e-5, out=None):
+    _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "row_stats: x must be bf16 [M, D]")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, 2), device=x.device, dtype=f32)
+    N.check(N.load().vlmclip_row_stats_bf16(N.ptr(x), x.stride(0), N.ptr(out), M, D, float(eps), N.stream()),
+            "vlmclip_row_stats_bf16")
+    return out
+
+
+def im2col(pixels, patch: int, out=None):
+    _req(pixels.dim() == 4 and pixels.shape[1] == 3 and pixels.is_contiguous(), "im2col: pixels must be [B,3,H,W]")
+    _req(pixels.dtype in (f32, bf16), "im2col: pixels must be fp32 or bf16")
+    B, _, H, W = pixels.shape
+    K = 3 * patch * patch
+    Kpad = (K + 63) // 64 * 64
+    rows = B * (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty((rows, Kpad), device=pixels.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_im2col_patches(N.ptr(pixels), 1 if pixels.dtype == bf16 else 0, N.ptr(out), B, H, W, patch,
+                                        N.stream()), "vlmclip_im2col_patches")
+    return out
+
+
+def vision_embed_ln(patch_f32, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
+    D = pos.shape[1]
+    _req(patch_f32.dtype == f32 and patch_f32.shape == (B * (S - 1), D) and patch_f32.is_contiguous(),
+         "vision_embed_ln: patch must be fp32 [B*(S-1), D]")
+    if out is None:
+        out = torch.empty((B * S, D), device=pos.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_vision_embed_ln(N.ptr(patch_f32), N.ptr(cls), N.ptr(pos), N.ptr(gamma), N.ptr(beta),
+                                         N.ptr(out), B, S, D, float(eps), N.stream()), "vlmclip_vision_embed_ln")
+    return out
+
+
+def text_embed(ids, tok, pos, out=None):
+    _req(ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous(), "text_embed: ids must be int64 [B,S]")
+    B, S = ids.shape
+    V, D = tok.shape
+    _req(pos.shape[0] >= S, "text_embed: sequence longer than the position table")
+    if out is None:
+        out = torch.empty((B * S, D), device=ids.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_text_embed(N.ptr(ids), N.ptr(tok), 1 if tok.dtype == bf16 else 0, N.ptr(pos), N.ptr(out), B,
+                                    S, D, V, N.stream()), "vlmclip_text_embed")
+    return out
+
+
+def attention(qkv, B: int, S: int, H: int, causal=False, key_mask=None, scale=None, out=None):
+    _req(qkv.dtype == bf16 and qkv.shape == (B * S, 3 * H * 64) and qkv.is_contiguous(),
+         "attention: qkv must be contiguous bf16 [B*S, 3*H*64]")
+    if key_mask is not None:
+        _req(key_mask.dtype == torch.uint8 and key_mask.shape == (B, S) and key_mask.is_contiguous(),
+             "attention: key_mask must be uint8 [B,S]")
+    if out is None:
+        out = torch.empty((B * S, H * 64), device=qkv.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_attention_fwd(N.ptr(qkv), N.ptr(out), N.ptr(key_mask), B, S, H, 1 if causal else 0,
+                                       float(scale if scale is not None else 64 ** -0.5), N.stream()),
+        "vlmclip_attention_fwd")
+    return out
+
+
+def gather_rows_f32(x, rows: int, ld: int, D: int):
+    """y[r] = float(x.flat[r*ld : r*ld + D]) — the token-0 slice of a [B*S, D] bf16 activation."""
+    out = torch.empty((rows, D), device=x.device, dtype=f32)
+    N.check(N.load().vlmclip_gather_rows_bf16_to_f32(N.ptr(x), ld, N.ptr(out), rows, D, N.stream()),
+            "vlmclip_gather_rows_bf16_to_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- adapters
+class _AdapterFn(torch.autograd.Function):
+    """Fused bottleneck adapter (vlmclip_adapter_fwd / vlmclip_adapter_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, gamma, beta, hmask, act, post, alpha, eps, ldx, rows):
+        D = W1.shape[1]
+        A = W1.shape[0]
+        x_bf16 = x.dtype == bf16
+        y = torch.empty((rows, D), device=W1.device, dtype=f32)
+        N.check(
+            N.load().vlmclip_adapter_fwd(N.ptr(x), 1 if x_bf16 else 0, ldx, N.ptr(W1), N.ptr(b1), N.ptr(W2),
+                                         N.ptr(b2), N.ptr(gamma), N.ptr(beta), N.ptr(hmask), N.ptr(y), rows, D, A,
+                                         act, post, float(alpha), float(eps), N.stream()), "vlmclip_adapter_fwd")
+        ctx.save_for_backward(x, W1, b1, W2, b2, gamma, beta, hmask)
+        ctx.cfg = (act, post, float(alpha), float(eps), ldx, rows, D, A, x_bf16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W1, b1, W2, b2, gamma, beta, hmask = ctx.saved_tensors
+        act, post, alpha, eps, ldx, rows, D, A, x_bf16 = ctx.cfg
+        dy = dy.contiguous()
+        lib = N.load()
+        dev = W1.device
+        ws = torch.empty(lib.vlmclip_adapter_bwd_workspace(rows, D, A), device=dev, dtype=f32)
+        dW1, db1 = torch.empty_like(W1), torch.empty_like(b1)
+        dW2, db2 = torch.empty_like(W2), torch.empty_like(b2)
+        has_ln = post == N.POST_RESIDUAL_LN
+        dgamma = torch.empty_like(gamma) if has_ln else None
+        dbeta = torch.empty_like(beta) if has_ln else None
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty((rows, D), device=dev, dtype=f32) if need_dx else None
+        N.check(
+            lib.vlmclip_adapter_bwd(N.ptr(x), 1 if x_bf16 else 0, ldx, N.ptr(W1), N.ptr(b1), N.ptr(W2), N.ptr(b2),
+                                    N.ptr(gamma), N.ptr(beta), N.ptr(hmask), N.ptr(dy), N.ptr(dW1), N.ptr(db1),
+                                    N.ptr(dW2), N.ptr(db2), N.ptr(dgamma), N.ptr(dbeta), N.ptr(dx), N.ptr(ws), rows,
+                                    D, A, act, post, alpha, eps, N.stream()), "vlmclip_adapter_bwd")
+        if need_dx:
+            if x.shape != dx.shape or x.dtype != f32:
+                # strided / bf16 views are only used on the frozen-backbone path, which never asks for dx
+                raise N.NativeError("adapter dx is only available for contiguous fp32 inputs")
+        return dx, dW1, db1, dW2, db2, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def adapter(x, W1, b1, W2, b2, gamma=None, beta=None, *, act, post, alpha=0.0, eps=1e-5, hmask=None, ldx=None,
+            rows=None):
+    """y[rows, D] = post(act(x W1^T + b1) W2^T + b2, x).  `x` may be a wider buffer read with row stride `ldx`."""
+    D = W1.shape[1]
+    if rows is None:
+        _req(x.dim() == 2 and x.shape[1] == D and x.stride(1) == 1, "adapter: x must be [R, D]")
+        rows, ldx = x.shape[0], x.stride(0)
+    for t in (W1, b1, W2, b2):
+        _req(t.dtype == f32 and t.is_contiguous(), "adapter: weights must be contiguous fp32")
+    return _AdapterFn.apply(x, W1, b1, W2, b2, gamma, beta, hmask, int(act), int(post), alpha, eps, int(ldx),
+                            int(rows))
+
+
+class _LinearF32Fn(torch.autograd.Function):
+    """y = x W^T (+ b) with a FROZEN weight: backward only produces dx (projection heads, HF:784-785)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        R, K = x.shape
+        Nn = W.shape[0]
+        y = torch.empty((R, Nn), device=x.device, dtype=f32)
+        N.check(N.load().vlmclip_linear_f32(N.ptr(x), x.stride(0), N.ptr(W), N.ptr(b), N.ptr(y), R, Nn, K, N.stream()),
+                "vlmclip_linear_f32")
+        ctx.save_for_backward(W)
+        ctx.dims = (R, Nn, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (W,) = ctx.saved_tensors
+        R, Nn, K = ctx.dims
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dy = dy.contiguous()
+            dx = torch.empty((R, K), device=dy.device, dtype=f32)
+            N.check(N.load().vlmclip_linear_f32_dgrad(N.ptr(dy), N.ptr(W), N.ptr(dx), R, Nn, K, N.stream()),
+                    "vlmclip_linear_f32_dgrad")
+        return dx, None, None
+
+
+def linear_f32(x, W, b=None):
+    _req(x.dtype == f32 and x.dim() == 2 and x.stride(1) == 1, "linear_f32: x must be fp32 [R, K]")
+    _req(W.dtype == f32 and W.is_contiguous() and W.shape[1] == x.shape[1], "linear_f32: W must be fp32 [N, K]")
+    return _LinearF32Fn.apply(x, W, b)
+
+
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        R, P = x.shape
+        y = torch.empty_like(x)
+        N.check(N.load().vlmclip_l2norm_rows(N.ptr(x), N.ptr(y), R, P, N.stream()), "vlmclip_l2norm_rows")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        R, P = x.shape
+        dx = torch.empty_like(x)
+        N.check(N.load().vlmclip_l2norm_rows_bwd(N.ptr(x), N.ptr(dy.contiguous()), N.ptr(dx), R, P, N.stream()),
+                "vlmclip_l2norm_rows_bwd")
+        return dx
+
+
+def l2norm(x):
+    _req(x.dtype == f32 and x.dim() == 2 and x.is_contiguous(), "l2norm: x must be contiguous fp32 [R, P]")
+    return _L2NormFn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------- heads
+class _ClipLossFn(torch.autograd.Function):
+    """Symmetric InfoNCE over the (global) batch; gradients for rows [row0, row0 + nloc) only."""
+
+    @staticmethod
+    def forward(ctx, txt_local, img_local, txt_all, img_all, scale_exp, row0, want_logits):
+        Ng, P = txt_all.shape
+        nloc = txt_local.shape[0]
+        dev = txt_all.device
+        lib = N.load()
+        txt_n = torch.empty_like(txt_all)
+        img_n = torch.empty_like(img_all)
+        logits = torch.empty((Ng, Ng), device=dev, dtype=f32) if want_logits else None
+        loss = torch.empty((1,), device=dev, dtype=f32)
+        d_txt = torch.empty((nloc, P), device=dev, dtype=f32)
+        d_img = torch.empty((nloc, P), device=dev, dtype=f32)
+        ws = torch.empty(lib.vlmclip_clip_loss_workspace(Ng, P), device=dev, dtype=f32)
+        N.check(
+            lib.vlmclip_clip_loss(N.ptr(txt_all), N.ptr(img_all), float(scale_exp), N.ptr(txt_n), N.ptr(img_n),
+                                  N.ptr(logits), N.ptr(loss), N.ptr(d_txt), N.ptr(d_img), None, N.ptr(ws), Ng, P,
+                                  int(row0), nloc, N.stream()), "vlmclip_clip_loss")
+        ctx.save_for_backward(d_txt, d_img)
+        ctx.mark_non_differentiable(txt_n, img_n)
+        if logits is not None:
+            ctx.mark_non_differentiable(logits)
+            return loss[0], txt_n, img_n, logits
+        return loss[0], txt_n, img_n, torch.empty(0, device=dev)
+
+    @staticmethod
+    def backward(ctx, dloss, *_):
+        d_txt, d_img = ctx.saved_tensors
+        return d_txt * dloss, d_img * dloss, None, None, None, None, None
+
+
+def clip_loss(txt_local, img_local, logit_scale_exp: float, txt_all=None, img_all=None, row0: int = 0,
+              want_logits: bool = True):
+    """Returns (loss, txt_normalised_all, img_normalised_all, logits_per_text_all).
+
+    txt_all / img_all: the all-gathered un-normalised features under data parallelism (default: the local ones).
+    """
+    if txt_all is None:
+        txt_all, img_all, row0 = txt_local.detach(), img_local.detach(), 0
+    for t in (txt_local, img_local, txt_all, img_all):
+        _req(t.dtype == f32 and t.dim() == 2 and t.is_contiguous(), "clip_loss: features must be contiguous fp32 [N, P]")
+    return _ClipLossFn.apply(txt_local, img_local, txt_all, img_all, float(logit_scale_exp), int(row0), want_logits)
+
+
+class _ClassHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f_img, f_txt, scale, labels, soft):
+        B, P = f_img.shape
+        Cc = f_txt.shape[0]
+        dev = f_img.device
+        logits = torch.empty((B, Cc), device=dev, dtype=f32)
+        have_lab = labels is not None or soft is not None
+        loss = torch.zeros((1,), device=dev, dtype=f32)
+        d_img = torch.empty_like(f_img) if have_lab else None
+        d_txt = torch.empty_like(f_txt) if have_lab else None
+        ws = torch.empty(B * Cc + B, device=dev, dtype=f32) if have_lab else None
+        N.check(
+            N.load().vlmclip_class_head(N.ptr(f_img), N.ptr(f_txt), float(scale), N.ptr(labels), N.ptr(soft),
+                                        N.ptr(logits), None, N.ptr(loss) if have_lab else None, N.ptr(d_img),
+                                        N.ptr(d_txt), N.ptr(ws), B, Cc, P, 1, N.stream()), "vlmclip_class_head")
+        if have_lab:
+            ctx.save_for_backward(d_img, d_txt)
+        ctx.have_lab = have_lab
+        ctx.mark_non_differentiable(logits)
+        return loss[0], logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        if not ctx.have_lab:
+            raise N.NativeError("class_head: backward needs labels")
+        d_img, d_txt = ctx.saved_tensors
+        return d_img * dloss, d_txt * dloss, None, None, None
+
+
+def class_head_loss(f_img, f_txt, scale: float, labels=None, soft_labels=None):
+    """(loss, logits) of model_t.py:184-187: logits = scale * f_img f_txt^T, CE(logits, labels)."""
+    for t in (f_img, f_txt):
+        _req(t.dtype == f32 and t.dim() == 2 and t.is_contiguous(), "class_head: features must be contiguous fp32")
+    if labels is not None:
+        _req(labels.dtype == torch.int64 and labels.is_contiguous(), "class_head: labels must be int64")
+    if soft_labels is not None:
+        _req(soft_labels.dtype == f32 and soft_labels.is_contiguous(), "class_head: soft labels must be fp32")
+    return _ClassHeadFn.apply(f_img, f_txt, float(scale), labels, soft_labels)
+
+
+def class_head_probs(f_img, f_txt, scale: float, group: int = 1):
+    """softmax(scale * f_img f_txt^T) with an optional max over `group` prompts per class (forward only)."""
+    B, P = f_img.shape
+    Cc = f_txt.shape[0] // group
+    logits = torch.empty((B, Cc), device=f_img.device, dtype=f32)
+    probs = torch.empty((B, Cc), device=f_img.device, dtype=f32)
+    N.check(
+        N.load().vlmclip_class_head(N.ptr(f_img.contiguous()), N.ptr(f_txt.contiguous()), float(scale), None, None,
+                                    N.ptr(logits), N.ptr(probs), None, None, None, None, B, Cc, P, int(group),
+                                    N.stream()), "vlmclip_class_head")
+    return probs, logits
+
+
+# --------------------------------------------------------------------------------------------- optimiser
+class FusedAdamW:
+    """clip_grad_norm_ + AdamW over one flat fp32 arena (trainer.py:91-99), two launches, no host sync.
+
+    Parameters are re-pointed into a flat buffer (param.data becomes a view), and so are their .grad tensors,
+    so autograd accumulates straight into the arena the kernel reads.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=0.0):
+        self.params = [p for p in params]
+        _req(len(self.params) > 0, "FusedAdamW: empty parameter list")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.flat = torch.empty(n, device=dev, dtype=f32)
+        self.grad = torch.zeros(n, device=dev, dtype=f32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=f32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=f32)
+        off = 0
+        for p in self.params:
+            _req(p.dtype == f32 and p.device == dev, "FusedAdamW: parameters must be fp32 on one device")
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        self.lr = torch.full((1,), float(lr), device=dev, dtype=f32)
+        self._lr_on_device = float(lr)
+        self.betas, self.eps, self.weight_decay, self.max_grad_norm = betas, eps, weight_decay, max_grad_norm
+        self.step_t = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.grad_norm = torch.zeros((1,), device=dev, dtype=f32)
+        self.ws = torch.empty(1024, device=dev, dtype=f32)
+        # torch.optim-compatible surface used by LR schedulers
+        self.param_groups = [{"params": self.params, "lr": float(lr), "initial_lr": float(lr)}]
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:  # keep .grad pointing into the arena even if someone set it to None
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+
+    def set_lr(self, lr: float):
+        self.param_groups[0]["lr"] = float(lr)
+
+    def step(self):
+        lr_host = float(self.param_groups[0]["lr"])  # an LR scheduler writes here (trainer.py:58-62,99)
+        if lr_host != self._lr_on_device:
+            self.lr.fill_(lr_host)
+            self._lr_on_device = lr_host
+        N.check(
+            N.load().vlmclip_adamw_clip_step(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg),
+                                             N.ptr(self.exp_avg_sq), self.n, N.ptr(self.lr), self.betas[0],
+                                             self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
+                                             N.ptr(self.step_t), N.ptr(self.grad_norm), N.ptr(self.ws), N.stream()),
+            "vlmclip_adamw_clip_step")
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_t.clone(),
+                "lr": self.param_groups[0]["lr"]}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_t.copy_(sd["step"])
+        self.set_lr(sd["lr"])
