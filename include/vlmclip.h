@@ -71,6 +71,10 @@ int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */
 int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
                            const float* beta, float* stats_out, int M, int D, float eps, void* stream);
+/* Same, writing fp32 (used on the few pooled rows that feed the fp32 trainable path: token 0 through
+ * final_layer_norm, model_m.py:86,102; CLS through post_layernorm, HF:686).  x rows may be strided (ldx). */
+int vlmclip_layernorm_bf16_f32out(const void* x, int64_t ldx, float* y, int64_t ldy, const float* gamma,
+                                  const float* beta, int M, int D, float eps, void* stream);
 /* Row statistics only (mean, rstd) for the LN-folded GEMM epilogue. */
 int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, int D, float eps, void* stream);
 

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "vlmclip_launch_count": (_i64, []),
     "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vlmclip_layernorm_bf16": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
+    "vlmclip_layernorm_bf16_f32out": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _f, _p]),
     "vlmclip_row_stats_bf16": (_i, [_p, _i64, _p, _i, _i, _f, _p]),
     "vlmclip_im2col_patches": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "vlmclip_vision_embed_ln": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),

@@ -9,9 +9,14 @@
 //   warp 1 (1 thread)  tcgen05.mma issuer (cta_group::1, M=128, N=BLOCK_N, K=16 x 4 per stage),
 //                      fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the
 //                      epilogue of tile i overlaps the main loop of tile i+1.
-//   warp 2             TMEM allocator / deallocator.
-//   warps 4..7         epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> registers ->
-//                      LN-fold / bias / activation / residual -> bf16 (or fp32) -> global.
+//   warp 2             TMEM allocator / deallocator; lane 0 = panel manager of epilogue group 0.
+//   warp 3 (1 thread)  panel manager of epilogue group 1.
+//   warps 4..11        epilogue, two groups of 4 warps (each group covers the 128 accumulator rows and
+//                      owns every other 64-column quarter of the tile): tcgen05.ld -> registers ->
+//                      LN-fold / bias / activation (vectors staged in smem once per tile) -> + residual
+//                      (prefetched by TMA into a 128-B-swizzled 128x64 panel) -> bf16 written in place
+//                      into the panel -> TMA store.  Panel managers chain store -> wait-read -> next
+//                      residual load so global traffic of the epilogue is fully asynchronous.
 //   Tile order is n-fastest so the CTAs running at one moment share a few A row-blocks through L2.
 #include "common.cuh"
 
@@ -22,9 +27,12 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_GROUP_THREADS = 128;      // one group = 4 warps = all 128 accumulator rows
+constexpr int QUARTER_N = 64;               // staged epilogue unit: 128 rows x 64 columns (one swizzle panel)
+constexpr uint32_t EBUF_BYTES = BLOCK_M * QUARTER_N * 2;  // 16 KB
 
 struct GemmParams {
   void* C;
@@ -36,6 +44,7 @@ struct GemmParams {
   int M, N, K;
   int act;
   int out_fp32;
+  int staged;  // 1: residual in / result out go through swizzled smem panels and TMA (bf16 output only)
   int m_tiles, n_tiles, k_blocks;
 };
 
@@ -44,10 +53,11 @@ struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4;
-  static constexpr uint32_t TOTAL = BAR_OFFSET + NUM_BARS * 8 + 16;
-  static constexpr uint32_t DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
+  static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;          // 2 x 16 KB, 1024-aligned
+  static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EBUF_BYTES;   // bias[BLOCK_N], col_c[BLOCK_N] fp32
+  static constexpr uint32_t BAR_OFFSET = VEC_OFFSET + 2 * BLOCK_N * 4;
+  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 4;
+  static constexpr uint32_t DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -57,31 +67,75 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// v[0..7] = epilogue(acc) for 8 consecutive columns starting at tile-local column lc
+__device__ __forceinline__ void epi_math8(float* v, const float* sBias, const float* sColc, int lc, float a_scale,
+                                          float a_shift, bool has_bias, bool has_stats, int act) {
+  if (has_stats) {
+    // rstd*(acc - mean*c) + b  ==  fma(rstd, acc, fma(-mean*rstd, c, b))
+    const float4 c0 = *reinterpret_cast<const float4*>(sColc + lc);
+    const float4 c1 = *reinterpret_cast<const float4*>(sColc + lc + 4);
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (has_bias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sBias + lc);
+      const float4 b1 = *reinterpret_cast<const float4*>(sBias + lc + 4);
+      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+      bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(a_scale, v[j], fmaf(a_shift, cc[j], bb[j]));
+  } else if (has_bias) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sBias + lc);
+    const float4 b1 = *reinterpret_cast<const float4*>(sBias + lc + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += bb[j];
+  }
+  if (act != 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], act);
+  }
+}
+
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 or 512)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  constexpr int QUARTERS = BLOCK_N / QUARTER_N;
+  extern __shared__ __align__(1024) uint8_t smem[];
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * L::A_BYTES;
+  uint8_t* sE = smem + L::EBUF_OFFSET;
+  float* sBias = reinterpret_cast<float*>(smem + L::VEC_OFFSET);
+  float* sColc = sBias + BLOCK_N;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint64_t* res_full_bar = bars + 2 * STAGES + 4;   // [2] E buffer of group g is free (and holds the residual)
+  uint64_t* e_written_bar = bars + 2 * STAGES + 6;  // [2] group g has written its result panel
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzled tiles need a 1024-B aligned base
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.staged) {
+      tma_prefetch_desc(&tmC);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -91,6 +145,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], EPI_THREADS);
+      mbar_init(&res_full_bar[b], 1);
+      mbar_init(&e_written_bar[b], EPI_GROUP_THREADS);
     }
     fence_mbar_init();
   }
@@ -150,90 +206,181 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       abuf ^= 1u;
       if (abuf == 0) aphase ^= 1u;
     }
+  } else if ((warp == 2 || warp == 3) && lane == 0) {
+    // ===================== epilogue panel manager of group g =====================
+    // Owns E buffer g: TMA-stores the panel the group has written, then (once the store has read it) refills
+    // the buffer with the residual panel of the group's next quarter, or simply hands it back.
+    if (p.staged) {
+      const int g = warp - 2;
+      uint8_t* ebuf = sE + g * EBUF_BYTES;
+      uint32_t wphase = 0;
+      bool pending = false;
+      int prev_c0 = 0, prev_r0 = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile - m_blk * p.n_tiles;
+        for (int q = g; q < QUARTERS; q += 2) {
+          const int c0 = n_blk * BLOCK_N + q * QUARTER_N;
+          if (c0 >= p.N) continue;
+          if (pending) {
+            mbar_wait(&e_written_bar[g], wphase);
+            wphase ^= 1u;
+            tma_store_2d(&tmC, ebuf, prev_c0, prev_r0);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          if (p.residual != nullptr) {
+            mbar_arrive_expect_tx(&res_full_bar[g], EBUF_BYTES);
+            tma_load_2d(ebuf, &tmR, &res_full_bar[g], c0, m_blk * BLOCK_M);
+          } else {
+            mbar_arrive(&res_full_bar[g]);
+          }
+          pending = true;
+          prev_c0 = c0;
+          prev_r0 = m_blk * BLOCK_M;
+        }
+      }
+      if (pending) {
+        mbar_wait(&e_written_bar[g], wphase);
+        tma_store_2d(&tmC, ebuf, prev_c0, prev_r0);
+        tma_store_commit();
+      }
+      tma_store_wait<0>();  // all stores complete before the CTA (and its shared memory) goes away
+    }
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    uint32_t abuf = 0, aphase = 0;
+    // ===================== epilogue workers =====================
+    const int g = (warp - EPI_WARP0) >> 2;  // column group: quarters g, g+2
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+    const bool has_bias = p.bias != nullptr;
+    const bool has_stats = p.row_stats != nullptr;
+    uint8_t* ebuf = sE + g * EBUF_BYTES;
+    uint32_t abuf = 0, aphase = 0, rphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int row = m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
-      float mean = 0.f, rstd = 1.f;
-      if (p.row_stats != nullptr && row_ok) {
+      float a_scale = 1.f, a_shift = 0.f;
+      if (has_stats && row_ok) {
         const float2 st = *reinterpret_cast<const float2*>(p.row_stats + 2 * (int64_t)row);
-        mean = st.x;
-        rstd = st.y;
+        a_scale = st.y;
+        a_shift = -st.x * st.y;
       }
+      // ---- stage this tile's bias / col_c once (previous tile's readers are past the first barrier) ----
+      named_bar_sync(1, EPI_THREADS);
+      if (et < BLOCK_N) {
+        const int col = n_blk * BLOCK_N + et;
+        sBias[et] = (has_bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        sColc[et] = (has_stats && col < p.N) ? __ldg(p.col_c + col) : 0.f;
+      }
+      named_bar_sync(1, EPI_THREADS);
+
       mbar_wait(&tfull_bar[abuf], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + abuf * BLOCK_N;
+
+      if (p.staged) {
+        bool released = false;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the row-predicated stores
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_wait_ld();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= p.N) continue;  // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        // columns beyond N inside this chunk (N % 8 == 0): handled per 8-column group
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + g * 8;
-          if (col >= p.N) break;  // warp-uniform
-          if (p.row_stats != nullptr) {
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.col_c + col));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.col_c + col + 4));
-            const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] = rstd * (v[g * 8 + j] - mean * cc[j]);
+        for (int q = g; q < QUARTERS; q += 2) {
+          const int c0 = n_blk * BLOCK_N + q * QUARTER_N;
+          if (c0 >= p.N) continue;  // uniform across the CTA
+          uint32_t r0[32], r1[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + q * QUARTER_N, r0);
+          tmem_ld_32x32b_x32(taddr + q * QUARTER_N + 32, r1);
+          tmem_wait_ld();
+          if (q + 2 >= QUARTERS || c0 + 2 * QUARTER_N >= p.N) {
+            tcgen05_fence_before();
+            mbar_arrive(&tempty_bar[abuf]);  // last TMEM read of this tile: hand the accumulator back early
+            released = true;
           }
-          if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          mbar_wait(&res_full_bar[g], rphase);  // E buffer is ours (and holds the residual panel, if any)
+          rphase ^= 1u;
+          uint8_t* erow = ebuf + row_in_tile * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += bb[j];
-          }
-          if (p.act != 0) {
+          for (int pc = 0; pc < 8; ++pc) {
+            float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] = apply_act(v[g * 8 + j], p.act);
-          }
-          if (row_ok) {
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(pc < 4 ? r0[pc * 8 + j] : r1[(pc - 4) * 8 + j]);
+            epi_math8(v, sBias, sColc, q * QUARTER_N + pc * 8, a_scale, a_shift, has_bias, has_stats, p.act);
+            uint4* slot = reinterpret_cast<uint4*>(erow + ((pc ^ (row_in_tile & 7)) << 4));  // 128-B swizzle
             if (p.residual != nullptr) {
-              const uint4 rr = ld_nc_v4(p.residual + (int64_t)row * p.ldr + col);
-              v[g * 8 + 0] += bf16_lo(rr.x);
-              v[g * 8 + 1] += bf16_hi(rr.x);
-              v[g * 8 + 2] += bf16_lo(rr.y);
-              v[g * 8 + 3] += bf16_hi(rr.y);
-              v[g * 8 + 4] += bf16_lo(rr.z);
-              v[g * 8 + 5] += bf16_hi(rr.z);
-              v[g * 8 + 6] += bf16_lo(rr.w);
-              v[g * 8 + 7] += bf16_hi(rr.w);
+              const uint4 rr = *slot;
+              v[0] += bf16_lo(rr.x);
+              v[1] += bf16_hi(rr.x);
+              v[2] += bf16_lo(rr.y);
+              v[3] += bf16_hi(rr.y);
+              v[4] += bf16_lo(rr.z);
+              v[5] += bf16_hi(rr.z);
+              v[6] += bf16_lo(rr.w);
+              v[7] += bf16_hi(rr.w);
             }
-            if (p.out_fp32) {
-              float* out = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col;
-              *reinterpret_cast<float4*>(out) =
-                  make_float4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-              *reinterpret_cast<float4*>(out + 4) =
-                  make_float4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-            } else {
-              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col;
-              uint4 o;
-              o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-              o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-              o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-              o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-              st_v4(out, o);
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]);
+            o.w = pack_bf16x2(v[6], v[7]);
+            *slot = o;
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+          mbar_arrive(&e_written_bar[g]);
+        }
+        if (!released) {
+          tcgen05_fence_before();
+          mbar_arrive(&tempty_bar[abuf]);
+        }
+      } else {
+        // ---- direct path (fp32 output / narrow tiles): registers -> global ----
+#pragma unroll 1
+        for (int c = g; c < BLOCK_N / 32; c += 2) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_wait_ld();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (col0 >= p.N) continue;  // warp-uniform
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int col = col0 + gq * 8;
+            if (col >= p.N) break;  // warp-uniform (N % 8 == 0)
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
+            epi_math8(v, sBias, sColc, c * 32 + gq * 8, a_scale, a_shift, has_bias, has_stats, p.act);
+            if (row_ok) {
+              if (p.residual != nullptr) {
+                const uint4 rr = ld_nc_v4(p.residual + (int64_t)row * p.ldr + col);
+                v[0] += bf16_lo(rr.x);
+                v[1] += bf16_hi(rr.x);
+                v[2] += bf16_lo(rr.y);
+                v[3] += bf16_hi(rr.y);
+                v[4] += bf16_lo(rr.z);
+                v[5] += bf16_hi(rr.z);
+                v[6] += bf16_lo(rr.w);
+                v[7] += bf16_hi(rr.w);
+              }
+              if (p.out_fp32) {
+                float* out = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col;
+                *reinterpret_cast<float4*>(out) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(out + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col;
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                st_v4(out, o);
+              }
             }
           }
         }
+        tcgen05_fence_before();
+        mbar_arrive(&tempty_bar[abuf]);
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tempty_bar[abuf]);
       abuf ^= 1u;
       if (abuf == 0) aphase ^= 1u;
     }
@@ -242,6 +389,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
+    __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -265,7 +413,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] (ld elements) -> 2-D map with box [box_rows x 64 cols], 128-B swizzle
+// bf16 row-major [rows, cols] (ld elements) -> 2-D map with box [box_rows x 64 cols], 128-B swizzle.
+// Used for the K-major operand tiles and for the 128 x 64 result / residual panels of the epilogue.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
@@ -288,7 +437,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t col
 }
 
 template <int BLOCK_N, int STAGES>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   static bool attr_set = false;  // benign race: setting the attribute twice is harmless
   if (!attr_set) {
@@ -299,7 +449,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, c
   p.n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tn_kernel<BLOCK_N, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, p);
+  gemm_bf16_tn_kernel<BLOCK_N, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   return report_cuda(cudaGetLastError(), "gemm_bf16_tn_kernel launch");
 }
 
@@ -348,13 +498,24 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 
   const bool wide = N > 128;
   const int block_n = wide ? 256 : 128;
-  CUtensorMap tmA, tmB;
+  p.staged = out_fp32 ? 0 : 1;
+  CUtensorMap tmA, tmB, tmC, tmR;
   int rc = make_tmap_bf16(&tmA, A, M, K, lda, BLOCK_M);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, W, N, K, ldw, block_n);
   if (rc) return rc;
+  tmC = tmA;
+  tmR = tmA;
+  if (p.staged) {
+    rc = make_tmap_bf16(&tmC, C, M, N, ldc, BLOCK_M);
+    if (rc) return rc;
+    if (residual) {
+      rc = make_tmap_bf16(&tmR, residual, M, N, ldr, BLOCK_M);
+      if (rc) return rc;
+    }
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   count_launch(1);
-  if (wide) return launch_gemm<256, 4>(tmA, tmB, p, s);
-  return launch_gemm<128, 6>(tmA, tmB, p, s);
+  if (wide) return launch_gemm<256, 4>(tmA, tmB, tmC, tmR, p, s);
+  return launch_gemm<128, 6>(tmA, tmB, tmC, tmR, p, s);
 }

@@ -56,10 +56,10 @@ __device__ __forceinline__ void row_mean_rstd(float (*v)[8], int nvec_lane_valid
   rstd = rsqrtf(q / (float)D + eps);
 }
 
-// MODE 0: y = LN(x) (+stats)   MODE 1: stats only
+// MODE 0: y = LN(x) bf16 (+stats)   MODE 1: stats only   MODE 2: y = LN(x) written as fp32
 template <int MODE>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy,
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, void* __restrict__ y_, int64_t ldy,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ stats, int M,
                  int D, float eps) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
@@ -84,8 +84,9 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16
     stats[2 * (int64_t)row] = mean;
     stats[2 * (int64_t)row + 1] = rstd;
   }
-  if (MODE == 0) {
-    __nv_bfloat16* yr = y + (int64_t)row * ldy;
+  if (MODE == 0 || MODE == 2) {
+    __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(y_) + (int64_t)row * ldy;
+    float* yf = reinterpret_cast<float*>(y_) + (int64_t)row * ldy;
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
       if (valid[i]) {
@@ -99,7 +100,12 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
-        st_v4(yr + c, pack8(o));
+        if (MODE == 0) {
+          st_v4(yr + c, pack8(o));
+        } else {
+          *reinterpret_cast<float4*>(yf + c) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(yf + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
   }
@@ -243,8 +249,24 @@ extern "C" int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64
   const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   count_launch(1);
   layernorm_kernel<0><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, gamma, beta, stats_out, M, D, eps);
+      (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, stats_out, M, D, eps);
   return report_cuda(cudaGetLastError(), "layernorm_kernel launch");
+}
+
+extern "C" int vlmclip_layernorm_bf16_f32out(const void* x, int64_t ldx, float* y, int64_t ldy, const float* gamma,
+                                             const float* beta, int M, int D, float eps, void* stream) {
+  VLMCLIP_CHECK_ARG(x && y && gamma && beta, "layernorm_f32out: null pointer");
+  VLMCLIP_CHECK_ARG(M > 0 && D > 0 && D % 8 == 0 && D <= MAX_VEC * 256, "layernorm_f32out: D=%d must be a multiple of 8, <= %d",
+                    D, MAX_VEC * 256);
+  VLMCLIP_CHECK_ARG(ldx % 8 == 0 && ldy % 4 == 0 && ldx >= D && ldy >= D, "layernorm_f32out: bad leading dimension");
+  VLMCLIP_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 &&
+                        (uintptr_t)beta % 16 == 0,
+                    "layernorm_f32out: pointers must be 16-byte aligned");
+  const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  count_launch(1);
+  layernorm_kernel<2><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, nullptr, M, D, eps);
+  return report_cuda(cudaGetLastError(), "layernorm_kernel<f32out> launch");
 }
 
 extern "C" int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, int D, float eps,

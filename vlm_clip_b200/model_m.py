@@ -1,0 +1,236 @@
+"""B200-native mirror of the reference's Track-M model (reference: model_m.py).
+
+`CLIPWithAdapters` keeps the reference's constructor, attributes (`clip`, `processor`, `text_adapter`,
+`vision_adapter`, `shared_adapters`), methods and return dicts, so `trainer.py` / `train.py` / `utest.py` work
+against it unchanged.  What changes is who does the arithmetic:
+
+  frozen towers     vlm_clip_b200.towers.NativeClipTowers (tcgen05 GEMMs, flash attention, folded LayerNorm)
+  adapters          one fused kernel per adapter, evaluated on token 0 only — the reference applies the adapter
+                    to all tokens and then keeps `[:, 0, :]` (model_m.py:87-90,102,116-118,122); the adapter is
+                    position-wise, so this is result-identical
+  projections       fp32 linear with an input-gradient kernel (weights frozen)
+  loss              fused L2-normalise + scaled similarity + symmetric cross-entropy + gradient (model_m.py:146-171)
+
+Reference quirks reproduced on purpose: text pooling takes token 0 (BOS), not EOS; the vision
+adapter sees the states BEFORE post_layernorm and post_layernorm is never applied; `forward` returns normalised
+features with the loss and un-normalised ones without it.
+
+Data parallelism (new): after `enable_data_parallel()`, each rank all-gathers the un-normalised
+features, evaluates the global N x N loss and differentiates only its own rows (exact dL_global/d local).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import ops
+from .adapter.clip_adapter import SharedMHSAttentionAdapter, TextAdapter, VisionAdapter
+from .towers import NativeClipTowers
+
+
+def _load_clip(name):
+    from transformers.models.clip import CLIPModel
+
+    return CLIPModel.from_pretrained(name)
+
+
+def _load_processor(name):
+    from transformers.models.clip import CLIPProcessor
+
+    try:
+        return CLIPProcessor.from_pretrained(name)
+    except Exception as e:  # offline box: the processor is host-side preprocessing, not part of the hot path
+        warnings.warn(f"CLIPProcessor.from_pretrained({name!r}) failed ({type(e).__name__}); .processor is None")
+        return None
+
+
+class CLIPWithAdapters(nn.Module):
+    """CLIP model with text and vision adapters (reference: model_m.py:10-248)."""
+
+    def __init__(
+        self,
+        clip_model_name="openai/clip-vit-base-patch32",
+        text_adapter_size=256,
+        vision_adapter_size=256,
+        shared_adapter_layers=2,
+        freeze_clip=True,
+        use_text_adapter=True,
+        use_vision_adapter=True,
+        use_shared_adapters=True,
+        *,
+        clip=None,
+        processor=None,
+    ):
+        super().__init__()
+        # `clip=` / `processor=` are extensions: a ready CLIPModel (e.g. random-init on an offline box)
+        self.clip = clip if clip is not None else _load_clip(clip_model_name)
+        self.processor = processor if processor is not None else (None if clip is not None else _load_processor(clip_model_name))
+
+        text_hidden_size = self.clip.text_model.config.hidden_size
+        vision_hidden_size = self.clip.vision_model.config.hidden_size
+
+        self.use_text_adapter = use_text_adapter
+        self.use_vision_adapter = use_vision_adapter
+        self.use_shared_adapters = use_shared_adapters
+
+        self.text_adapter = None
+        self.vision_adapter = None
+        self.shared_adapters = None
+        if self.use_text_adapter:
+            self.text_adapter = TextAdapter(text_hidden_size, text_adapter_size)
+        if self.use_vision_adapter:
+            self.vision_adapter = VisionAdapter(vision_hidden_size, vision_adapter_size)
+        if self.use_shared_adapters:
+            self.shared_adapters = nn.ModuleList(
+                [SharedMHSAttentionAdapter(text_hidden_size, vision_hidden_size) for _ in range(shared_adapter_layers)])
+
+        if freeze_clip:
+            self._freeze_clip_parameters()
+
+        self._towers = None
+        self._towers_key = None
+        self._dp_group = None
+        self._dp_enabled = False
+
+    # ------------------------------------------------------------------ reference API
+    def _freeze_clip_parameters(self):
+        for param in self.clip.parameters():
+            param.requires_grad = False
+
+    def _unfreeze_clip_parameters(self):
+        for param in self.clip.parameters():
+            param.requires_grad = True
+
+    # ------------------------------------------------------------------ native backbone
+    def _backbone(self) -> NativeClipTowers:
+        p = next(self.clip.parameters())
+        if p.device.type != "cuda":
+            raise N.NativeError("CLIPWithAdapters runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda')")
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.clip.parameters()):
+            raise N.NativeError("full fine-tuning (freeze_clip=False) needs the backbone backward kernels, which are "
+                                "not built yet (BASELINE config 5); keep the CLIP weights frozen")
+        key = (str(p.device), p.data_ptr(), p._version)
+        if self._towers is None or self._towers_key != key:
+            self._towers = NativeClipTowers(self.clip, p.device)
+            self._towers_key = key
+        return self._towers
+
+    def refresh_backbone(self):
+        """Re-pack the frozen CLIP weights (call after loading new backbone weights in place)."""
+        self._towers = None
+
+    def enable_data_parallel(self, group=None, enabled: bool = True):
+        """Global-batch contrastive loss over `group` (default world): all-gather of features, local-row gradients."""
+        self._dp_group = group
+        self._dp_enabled = enabled
+
+    def get_text_features(self, input_ids, attention_mask):
+        """Text features with adapter: fp32 [B, P] (reference: model_m.py:77-105)."""
+        if self.use_shared_adapters:
+            # raise through the adapter so the message names the missing kernel
+            self.shared_adapters[0](None, None)
+        bb = self._backbone()
+        B, S = input_ids.shape
+        hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
+        # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32
+        tok0 = ops.layernorm_rows_f32(hidden, bb.final_ln_w, bb.final_ln_b, bb.eps_t, rows=B, ldx=S * bb.Dt)
+        if self.use_text_adapter:
+            tok0 = self.text_adapter(tok0)
+        return ops.linear_f32(tok0, bb.text_projection)
+
+    def get_image_features(self, pixel_values):
+        """Image features with adapter: fp32 [B, P] (reference: model_m.py:107-125)."""
+        bb = self._backbone()
+        B = pixel_values.shape[0]
+        hidden = bb.vision_hidden(pixel_values)  # bf16 [B*S, Dv], pre post_layernorm
+        if self.use_vision_adapter:
+            cls = self.vision_adapter.forward_token0(hidden, B, bb.Sv)
+        else:
+            cls = ops.gather_rows_f32(hidden, B, bb.Sv * bb.Dv, bb.Dv)
+        return ops.linear_f32(cls, bb.visual_projection)
+
+    def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True):
+        """Same contract as the reference (model_m.py:127-176): 5-key dict with the loss, 2-key dict without."""
+        if input_ids is not None and attention_mask is not None:
+            text_features = self.get_text_features(input_ids, attention_mask)
+        else:
+            text_features = None
+        if pixel_values is not None:
+            image_features = self.get_image_features(pixel_values)
+        else:
+            image_features = None
+
+        if return_loss and text_features is not None and image_features is not None:
+            scale = self._logit_scale_exp()
+            txt_all = img_all = None
+            row0 = 0
+            if self._dp_enabled:
+                import torch.distributed as dist
+
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._dp_group) > 1:
+                    ws = dist.get_world_size(self._dp_group)
+                    rank = dist.get_rank(self._dp_group)
+                    B, P = text_features.shape
+                    both = torch.cat([text_features.detach(), image_features.detach()], dim=1).contiguous()
+                    gathered = torch.empty((ws * B, 2 * P), device=both.device, dtype=both.dtype)
+                    dist.all_gather_into_tensor(gathered, both, group=self._dp_group)
+                    txt_all = gathered[:, :P].contiguous()
+                    img_all = gathered[:, P:].contiguous()
+                    row0 = rank * B
+            loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0)
+            return {
+                "loss": loss,
+                "text_features": t_n,
+                "image_features": i_n,
+                "logits_per_text": logits_per_text,
+                "logits_per_image": logits_per_text.t(),
+            }
+        return {"text_features": text_features, "image_features": image_features}
+
+    def _logit_scale_exp(self) -> float:
+        # logit_scale is a frozen scalar parameter: cache exp() on the host, re-read only when it is modified
+        ls = self.clip.logit_scale
+        key = (ls.data_ptr(), ls._version)
+        if getattr(self, "_ls_key", None) != key:
+            self._ls_val = float(ls.detach().exp().item())
+            self._ls_key = key
+        return self._ls_val
+
+    # ------------------------------------------------------------------ checkpoints (reference: model_m.py:178-248)
+    def save_adapter_weights(self, save_path):
+        adapter_state_dict = {}
+        if self.use_text_adapter:
+            adapter_state_dict["text_adapter"] = self.text_adapter.state_dict()
+        if self.use_vision_adapter:
+            adapter_state_dict["vision_adapter"] = self.vision_adapter.state_dict()
+        if self.use_shared_adapters:
+            adapter_state_dict["shared_adapters"] = self.shared_adapters.state_dict()
+        if not adapter_state_dict:
+            raise ValueError("No adapters enabled to save")
+        os.makedirs(os.path.dirname(save_path), exist_ok=True)
+        torch.save(adapter_state_dict, save_path)
+        print(f"Adapter weights saved to {save_path}")
+        print(f"Saved adapters: {list(adapter_state_dict.keys())}")
+
+    def load_adapter_weights(self, load_path):
+        if not os.path.exists(load_path):
+            raise FileNotFoundError(f"No adapter weights found at {load_path}")
+        adapter_state_dict = torch.load(load_path, map_location=next(self.parameters()).device)
+        for key, flag, module in (("text_adapter", self.use_text_adapter, self.text_adapter),
+                                  ("vision_adapter", self.use_vision_adapter, self.vision_adapter),
+                                  ("shared_adapters", self.use_shared_adapters, self.shared_adapters)):
+            pretty = {"text_adapter": "Text adapter", "vision_adapter": "Vision adapter",
+                      "shared_adapters": "Shared adapter"}[key]
+            if key in adapter_state_dict:
+                if not flag:
+                    raise ValueError(f"{pretty} weights found but {pretty.lower()} is not enabled")
+                # copy_ into the existing storage: parameters may live in the fused optimiser's flat arena
+                module.load_state_dict(adapter_state_dict[key])
+            elif flag:
+                raise ValueError(f"{pretty} is enabled but no weights found in checkpoint")
+        print(f"Adapter weights loaded from {load_path}")
+        print(f"Loaded adapters: {list(adapter_state_dict.keys())}")

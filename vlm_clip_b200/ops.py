@@ -53,6 +53,19 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     return out
 
 
+def layernorm_rows_f32(x, gamma, beta, eps=1e-5, rows=None, ldx=None):
+    """fp32 LayerNorm of `rows` rows of a bf16 buffer read with row stride `ldx` (e.g. token 0 of every sequence)."""
+    _req(x.dtype == bf16 and x.is_contiguous(), "layernorm_rows_f32: x must be contiguous bf16")
+    D = gamma.shape[0]
+    if rows is None:
+        rows, ldx = x.shape[0], x.stride(0)
+    out = torch.empty((rows, D), device=x.device, dtype=f32)
+    N.check(
+        N.load().vlmclip_layernorm_bf16_f32out(N.ptr(x), int(ldx), N.ptr(out), D, N.ptr(gamma), N.ptr(beta), int(rows),
+                                               D, float(eps), N.stream()), "vlmclip_layernorm_bf16_f32out")
+    return out
+
+
 def row_stats(x, eps=1e-5, out=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "row_stats: x must be bf16 [M, D]")
     M, D = x.shape

@@ -1,0 +1,227 @@
+"""Frozen CLIP towers executed by the sm_100a library (the L1 layer of SURVEY.md §1).
+
+`NativeClipTowers` takes a HuggingFace `CLIPModel` purely as a weight container, packs its weights once
+(bf16 matrices for the tensor cores, fp32 vectors, q/k/v fused into one [3D, D] matrix, LayerNorm folded
+into the following dense layer) and replays the arithmetic of
+
+    CLIPVisionTransformer.forward   HF modeling_clip.py:667-691  (embeddings :202-218, pre_layrnorm :677)
+    CLIPTextTransformer.forward     HF modeling_clip.py:531-589  (embeddings :234-258, causal+padding mask :546-551)
+    CLIPEncoderLayer.forward        HF modeling_clip.py:363-384  (attention :300-336, MLP :347-351)
+
+with one kernel per fused step:
+
+    row_stats(x) -> [QKV GEMM: LN1 folded, bias] -> attention -> [out-proj GEMM: bias + residual, in place]
+    row_stats(x) -> [fc1 GEMM: LN2 folded, bias, quick_gelu] -> [fc2 GEMM: bias + residual, in place]
+
+LayerNorm folding:  LN(x) W^T + b = rstd * (x (g*W)^T - mean * c) + (beta W^T + b),  c_n = sum_k (g*W)[n,k],
+so the dense layer reads the raw bf16 residual stream and its epilogue applies the row statistics; the
+normalised activations are never written to HBM.  The backbone is frozen (model_m.py:64-70), so there is no
+backward through these layers.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _native as N
+from . import ops
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class _Layer:
+    qkv_w: torch.Tensor  # [3D, D] bf16, gamma1 folded
+    qkv_b: torch.Tensor  # [3D] fp32: beta1 W^T + b
+    qkv_c: torch.Tensor  # [3D] fp32: row sums of the folded bf16 weight
+    out_w: torch.Tensor
+    out_b: torch.Tensor
+    fc1_w: torch.Tensor  # [F, D] bf16, gamma2 folded
+    fc1_b: torch.Tensor
+    fc1_c: torch.Tensor
+    fc2_w: torch.Tensor
+    fc2_b: torch.Tensor
+    # unfolded copies for the explicit-LayerNorm path (fold_ln=False; used by tests to bound the fold's error)
+    ln1_w: torch.Tensor
+    ln1_b: torch.Tensor
+    ln2_w: torch.Tensor
+    ln2_b: torch.Tensor
+    qkv_w_raw: Optional[torch.Tensor] = None
+    qkv_b_raw: Optional[torch.Tensor] = None
+    fc1_w_raw: Optional[torch.Tensor] = None
+    fc1_b_raw: Optional[torch.Tensor] = None
+
+
+def _fold(W: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """Fold LN's affine into a following Linear.  Done once at pack time in fp32 (weight preparation, not hot path)."""
+    Wf = (W * gamma[None, :]).to(bf16)
+    c = Wf.float().sum(dim=1).contiguous()
+    d = (W @ beta + b).contiguous()
+    return Wf.contiguous(), d, c
+
+
+def _pack_layers(sd: Dict[str, torch.Tensor], prefix: str, dev, keep_raw: bool) -> List[_Layer]:
+    layers = []
+    l = 0
+    while f"{prefix}encoder.layers.{l}.layer_norm1.weight" in sd:
+        p = f"{prefix}encoder.layers.{l}."
+        g = lambda k: sd[p + k].detach().to(dev, f32)
+        Wqkv = torch.cat([g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"), g("self_attn.v_proj.weight")], 0)
+        bqkv = torch.cat([g("self_attn.q_proj.bias"), g("self_attn.k_proj.bias"), g("self_attn.v_proj.bias")], 0)
+        qkv_w, qkv_b, qkv_c = _fold(Wqkv, bqkv, g("layer_norm1.weight"), g("layer_norm1.bias"))
+        fc1_w, fc1_b, fc1_c = _fold(g("mlp.fc1.weight"), g("mlp.fc1.bias"), g("layer_norm2.weight"), g("layer_norm2.bias"))
+        layers.append(
+            _Layer(qkv_w, qkv_b, qkv_c, g("self_attn.out_proj.weight").to(bf16).contiguous(),
+                   g("self_attn.out_proj.bias").contiguous(), fc1_w, fc1_b, fc1_c,
+                   g("mlp.fc2.weight").to(bf16).contiguous(), g("mlp.fc2.bias").contiguous(),
+                   g("layer_norm1.weight").contiguous(), g("layer_norm1.bias").contiguous(),
+                   g("layer_norm2.weight").contiguous(), g("layer_norm2.bias").contiguous(),
+                   Wqkv.to(bf16).contiguous() if keep_raw else None, bqkv.contiguous() if keep_raw else None,
+                   g("mlp.fc1.weight").to(bf16).contiguous() if keep_raw else None,
+                   g("mlp.fc1.bias").contiguous() if keep_raw else None))
+        l += 1
+    return layers
+
+
+class NativeClipTowers:
+    """Device-resident packed weights + forward of both frozen towers."""
+
+    def __init__(self, clip, device=None, fold_ln: bool = True, keep_raw: bool = False):
+        N.load()
+        dev = torch.device(device) if device is not None else next(clip.parameters()).device
+        if dev.type != "cuda":
+            raise N.NativeError("NativeClipTowers needs a CUDA device: the towers only run on the sm_100a library")
+        self.device = dev
+        self.fold_ln = fold_ln
+        cfg = clip.config
+        vc, tc = cfg.vision_config, cfg.text_config
+        self.eps_v, self.eps_t = float(vc.layer_norm_eps), float(tc.layer_norm_eps)
+        self.Dv, self.Dt = vc.hidden_size, tc.hidden_size
+        self.Hv, self.Ht = vc.num_attention_heads, tc.num_attention_heads
+        self.patch, self.image = vc.patch_size, vc.image_size
+        self.Sv = (vc.image_size // vc.patch_size) ** 2 + 1
+        self.vocab = tc.vocab_size
+        self.max_pos = tc.max_position_embeddings
+        if self.Dv // self.Hv != 64 or self.Dt // self.Ht != 64:
+            raise ValueError("the attention kernel is specialised for head_dim = 64 (all OpenAI CLIP towers)")
+        if vc.hidden_act != "quick_gelu" or tc.hidden_act != "quick_gelu":
+            raise ValueError("only quick_gelu towers are supported (OpenAI CLIP); got %s/%s" % (vc.hidden_act, tc.hidden_act))
+        sd = clip.state_dict()
+        keep_raw = keep_raw or not fold_ln
+        g = lambda k: sd[k].detach().to(dev, f32).contiguous()
+        # ---- vision embeddings ----
+        w = g("vision_model.embeddings.patch_embedding.weight").reshape(self.Dv, -1)
+        K = w.shape[1]
+        Kpad = (K + 63) // 64 * 64
+        wp = torch.zeros(self.Dv, Kpad, device=dev, dtype=f32)
+        wp[:, :K] = w
+        self.patch_w = wp.to(bf16).contiguous()
+        self.cls = g("vision_model.embeddings.class_embedding")
+        self.pos_v = g("vision_model.embeddings.position_embedding.weight")
+        self.pre_ln_w, self.pre_ln_b = g("vision_model.pre_layrnorm.weight"), g("vision_model.pre_layrnorm.bias")
+        self.post_ln_w, self.post_ln_b = g("vision_model.post_layernorm.weight"), g("vision_model.post_layernorm.bias")
+        self.v_layers = _pack_layers(sd, "vision_model.", dev, keep_raw)
+        # ---- text embeddings ----
+        self.tok = g("text_model.embeddings.token_embedding.weight")
+        self.pos_t = g("text_model.embeddings.position_embedding.weight")
+        self.final_ln_w, self.final_ln_b = g("text_model.final_layer_norm.weight"), g("text_model.final_layer_norm.bias")
+        self.t_layers = _pack_layers(sd, "text_model.", dev, keep_raw)
+        # ---- heads (frozen, fp32: the trainable path runs in fp32) ----
+        self.visual_projection = g("visual_projection.weight")
+        self.text_projection = g("text_projection.weight")
+        self.eos_token_id = getattr(tc, "eos_token_id", 2)
+
+    # ------------------------------------------------------------------------------------------ encoder
+    def _encoder(self, x: torch.Tensor, layers: List[_Layer], B: int, S: int, H: int, eps: float, causal: bool,
+                 key_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        M, D = x.shape
+        F = layers[0].fc1_w.shape[0]
+        dev = x.device
+        qkv = torch.empty((M, 3 * D), device=dev, dtype=bf16)
+        att = torch.empty((M, D), device=dev, dtype=bf16)
+        hid = torch.empty((M, F), device=dev, dtype=bf16)
+        stats = torch.empty((M, 2), device=dev, dtype=f32)
+        xn = None if self.fold_ln else torch.empty((M, D), device=dev, dtype=bf16)
+        for L in layers:
+            if self.fold_ln:
+                ops.row_stats(x, eps, out=stats)
+                ops.gemm(x, L.qkv_w, bias=L.qkv_b, row_stats=stats, col_c=L.qkv_c, out=qkv)
+            else:
+                ops.layernorm(x, L.ln1_w, L.ln1_b, eps, out=xn)
+                ops.gemm(xn, L.qkv_w_raw, bias=L.qkv_b_raw, out=qkv)
+            ops.attention(qkv, B, S, H, causal=causal, key_mask=key_mask, out=att)
+            ops.gemm(att, L.out_w, bias=L.out_b, residual=x, out=x)  # x += out_proj(att): same thread reads & writes
+            if self.fold_ln:
+                ops.row_stats(x, eps, out=stats)
+                ops.gemm(x, L.fc1_w, bias=L.fc1_b, row_stats=stats, col_c=L.fc1_c, act=N.ACT_QUICK_GELU, out=hid)
+            else:
+                ops.layernorm(x, L.ln2_w, L.ln2_b, eps, out=xn)
+                ops.gemm(xn, L.fc1_w_raw, bias=L.fc1_b_raw, act=N.ACT_QUICK_GELU, out=hid)
+            ops.gemm(hid, L.fc2_w, bias=L.fc2_b, residual=x, out=x)
+        return x
+
+    # ------------------------------------------------------------------------------------------ towers
+    @torch.no_grad()
+    def vision_hidden(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """`vision_model(pixel_values).last_hidden_state` as bf16 [B*S, D] (NOT through post_layernorm, HF:684)."""
+        if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
+            raise ValueError("pixel_values must be [B, 3, H, W]")
+        if pixel_values.shape[2] != self.image or pixel_values.shape[3] != self.image:
+            raise ValueError(f"Input image size ({pixel_values.shape[2]}*{pixel_values.shape[3]}) doesn't match model "
+                             f"({self.image}*{self.image}).")  # same check as HF:204-207
+        if pixel_values.dtype not in (f32, bf16):
+            pixel_values = pixel_values.float()
+        pixel_values = pixel_values.contiguous()
+        B = pixel_values.shape[0]
+        cols = ops.im2col(pixel_values, self.patch)
+        patches = ops.gemm(cols, self.patch_w, out_fp32=True)  # [B*np, D] fp32
+        x = ops.vision_embed_ln(patches, self.cls, self.pos_v, self.pre_ln_w, self.pre_ln_b, B, self.Sv, self.eps_v)
+        return self._encoder(x, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None)
+
+    @torch.no_grad()
+    def text_hidden_pre_ln(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """Text encoder output BEFORE final_layer_norm, bf16 [B*S, D]."""
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [B, S]")
+        B, S = input_ids.shape
+        if S > self.max_pos:
+            raise ValueError(f"Sequence length must be less than max_position_embeddings (got `sequence length`: {S} "
+                             f"and max_position_embeddings: {self.max_pos}")
+        ids = input_ids.to(torch.int64).contiguous()
+        key_mask = None
+        if attention_mask is not None:
+            key_mask = (attention_mask != 0).to(torch.uint8).contiguous()
+        x = ops.text_embed(ids, self.tok, self.pos_t)
+        return self._encoder(x, self.t_layers, B, S, self.Ht, self.eps_t, True, key_mask)
+
+    @torch.no_grad()
+    def text_hidden(self, input_ids, attention_mask) -> torch.Tensor:
+        """`text_model(...).last_hidden_state` (after final_layer_norm, HF:562) as bf16 [B*S, D]."""
+        x = self.text_hidden_pre_ln(input_ids, attention_mask)
+        return ops.layernorm(x, self.final_ln_w, self.final_ln_b, self.eps_t)
+
+    # ------------------------------------------------------------------------------------------ pooled features
+    @torch.no_grad()
+    def image_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """CLIPModel.get_image_features (HF:829-863): projection(post_layernorm(CLS)), fp32 [B, P]."""
+        x = self.vision_hidden(pixel_values)
+        B = pixel_values.shape[0]
+        pooled = ops.layernorm_rows_f32(x, self.post_ln_w, self.post_ln_b, self.eps_v, rows=B, ldx=self.Sv * self.Dv)
+        return ops.linear_f32(pooled, self.visual_projection)
+
+    @torch.no_grad()
+    def text_features(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """CLIPModel.get_text_features (HF:793-827): projection of the final-LN state at the EOS position."""
+        x = self.text_hidden_pre_ln(input_ids, attention_mask)
+        B, S = input_ids.shape
+        ids = input_ids.to(torch.int)
+        if self.eos_token_id == 2:
+            eos = ids.argmax(dim=-1)  # HF:564-575 (index bookkeeping on [B,S] ints, not arithmetic on activations)
+        else:
+            eos = (ids == self.eos_token_id).int().argmax(dim=-1)
+        rows = (torch.arange(B, device=x.device) * S + eos).to(torch.int64)
+        picked = x.index_select(0, rows).contiguous()
+        pooled = ops.layernorm_rows_f32(picked, self.final_ln_w, self.final_ln_b, self.eps_t, rows=B, ldx=self.Dt)
+        return ops.linear_f32(pooled, self.text_projection)

@@ -1,0 +1,181 @@
+"""B200-native mirror of the reference trainer (reference: trainer.py).
+
+Same class, constructor and methods (`train`, `evaluate`, `save_model`, `load_model`) and the same selection of
+trainable parameters by name (trainer.py:39-43).  Differences, all on the optimiser tail:
+
+  * `clip_grad_norm_` + `AdamW.step` (trainer.py:95-98) are ONE fused two-launch kernel over a flat parameter
+    arena (ops.FusedAdamW), with no host synchronisation;
+  * the linear warm-up / decay schedule (trainer.py:58-62) is evaluated on the host and pushed as one scalar;
+  * `loss.item()` (trainer.py:101) is read every `log_every` steps instead of twice per step;
+  * under torch.distributed (one process per GPU) the contrastive loss is global and the adapter gradients are
+    all-reduced with SUM over NCCL before the clip — the 1/N already lives in the loss.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn  # noqa: F401  (kept for parity with the reference module's namespace)
+
+from . import ops
+from .model_m import CLIPWithAdapters  # noqa: F401
+
+
+def linear_schedule_multiplier(step: int, warmup_steps: int, total_steps: int) -> float:
+    """transformers.get_linear_schedule_with_warmup's lambda (reference: trainer.py:58-62)."""
+    if step < warmup_steps:
+        return float(step) / float(max(1, warmup_steps))
+    return max(0.0, float(total_steps - step) / float(max(1, total_steps - warmup_steps)))
+
+
+def _dist_world():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_world_size(), dist.get_rank()
+    return None, 1, 0
+
+
+class CLIPAdapterTrainer:
+    """Trainer class for fine-tuning CLIP with adapters (reference: trainer.py:11-167)."""
+
+    def __init__(
+        self,
+        model,
+        train_dataloader,
+        val_dataloader=None,
+        learning_rate=5e-5,
+        weight_decay=0.01,
+        warmup_steps=0,
+        max_grad_norm=1.0,
+        output_dir="./clip_adapter_checkpoints",
+        log_every=10,
+    ):
+        self.model = model
+        self.train_dataloader = train_dataloader
+        self.val_dataloader = val_dataloader
+        self.learning_rate = learning_rate
+        self.weight_decay = weight_decay
+        self.warmup_steps = warmup_steps
+        self.max_grad_norm = max_grad_norm
+        self.output_dir = output_dir
+        self.log_every = max(1, int(log_every))
+        os.makedirs(output_dir, exist_ok=True)
+
+        self.trainable_params = []
+        for name, param in model.named_parameters():
+            if "adapter" in name or "shared_adapters" in name:
+                self.trainable_params.append(param)
+        if not self.trainable_params:
+            raise ValueError("optimizer got an empty parameter list")  # what torch.optim.AdamW raises
+
+        self._optimizer = None
+        self._global_step = 0
+        self._total_steps = None
+        dist, world, _ = _dist_world()
+        if world > 1 and hasattr(model, "enable_data_parallel"):
+            model.enable_data_parallel()
+
+    # the fused optimiser needs the parameters on their final device, so it is created on first use
+    @property
+    def optimizer(self):
+        if self._optimizer is None:
+            self._optimizer = ops.FusedAdamW(self.trainable_params, lr=self.learning_rate,
+                                             weight_decay=self.weight_decay, max_grad_norm=self.max_grad_norm)
+        return self._optimizer
+
+    # ------------------------------------------------------------------ one step (reference: trainer.py:73-99)
+    def training_step(self, batch):
+        """forward -> zero_grad -> backward -> (all-reduce) -> clip + AdamW -> schedule.  Returns the loss tensor."""
+        device = next(self.model.parameters()).device
+        batch = {k: v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+        outputs = self.model(
+            input_ids=batch.get("input_ids"),
+            attention_mask=batch.get("attention_mask"),
+            pixel_values=batch.get("pixel_values"),
+            return_loss=True,
+        )
+        loss = outputs["loss"]
+        opt = self.optimizer
+        opt.zero_grad()
+        loss.backward()
+        dist, world, _ = _dist_world()
+        if world > 1:
+            dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM)
+        opt.step()
+        self._global_step += 1
+        if self._total_steps is not None:
+            opt.set_lr(self.learning_rate * linear_schedule_multiplier(self._global_step, self.warmup_steps,
+                                                                        self._total_steps))
+        return loss.detach()
+
+    def train(self, num_epochs, save_every=1, eval_every=1):
+        from tqdm import tqdm
+
+        self._total_steps = len(self.train_dataloader) * num_epochs
+        self._global_step = 0
+        self.optimizer.set_lr(self.learning_rate * linear_schedule_multiplier(0, self.warmup_steps, self._total_steps))
+        best_val_loss = float("inf")
+        _, _, rank = _dist_world()
+
+        for epoch in range(num_epochs):
+            self.model.train()
+            epoch_loss = None
+            with tqdm(total=len(self.train_dataloader), desc=f"Epoch {epoch + 1}/{num_epochs}",
+                      disable=rank != 0) as pbar:
+                for it, batch in enumerate(self.train_dataloader):
+                    loss = self.training_step(batch)
+                    epoch_loss = loss.clone() if epoch_loss is None else epoch_loss + loss
+                    pbar.update(1)
+                    if (it + 1) % self.log_every == 0:
+                        pbar.set_postfix({"loss": loss.item()})
+            avg_train_loss = (epoch_loss.item() if epoch_loss is not None else 0.0) / max(1, len(self.train_dataloader))
+            if rank == 0:
+                print(f"Epoch {epoch + 1} - Average training loss: {avg_train_loss:.4f}")
+
+            if self.val_dataloader is not None and (epoch + 1) % eval_every == 0:
+                val_loss = self.evaluate()
+                if rank == 0:
+                    print(f"Epoch {epoch + 1} - Validation loss: {val_loss:.4f}")
+                if val_loss < best_val_loss:
+                    best_val_loss = val_loss
+                    if rank == 0:
+                        self.save_model(os.path.join(self.output_dir, "best_adapter"))
+            if (epoch + 1) % save_every == 0 and rank == 0:
+                self.save_model(os.path.join(self.output_dir, f"adapter_epoch_{epoch + 1}"))
+        if rank == 0:
+            self.save_model(os.path.join(self.output_dir, "final_adapter"))
+
+    def evaluate(self):
+        assert self.val_dataloader is not None, "val_dataloader must not be None to run eval"
+        self.model.eval()
+        device = next(self.model.parameters()).device
+        val_loss = None
+        with torch.no_grad():
+            for batch in self.val_dataloader:
+                batch = {k: v.to(device) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+                outputs = self.model(
+                    input_ids=batch.get("input_ids"),
+                    attention_mask=batch.get("attention_mask"),
+                    pixel_values=batch.get("pixel_values"),
+                    return_loss=True,
+                )
+                val_loss = outputs["loss"].detach().clone() if val_loss is None else val_loss + outputs["loss"].detach()
+        return (val_loss.item() if val_loss is not None else 0.0) / len(self.val_dataloader)
+
+    def save_model(self, path):
+        self.model.save_adapter_weights(f"{path}.pt")
+
+    def load_model(self, path):
+        self.model.load_adapter_weights(f"{path}.pt")
+
+    # ------------------------------------------------------------------ true resume (not in the reference)
+    def save_training_state(self, path):
+        torch.save({"optimizer": self.optimizer.state_dict(), "global_step": self._global_step,
+                    "total_steps": self._total_steps}, path)
+
+    def load_training_state(self, path):
+        sd = torch.load(path, map_location=next(self.model.parameters()).device)
+        self.optimizer.load_state_dict(sd["optimizer"])
+        self._global_step = sd["global_step"]
+        self._total_steps = sd["total_steps"]
