@@ -160,8 +160,14 @@ int vlmclip_class_head(const float* f_img, const float* f_txt, float scale, cons
                        const float* soft_labels, float* logits, float* probs, float* loss, float* d_img,
                        float* d_txt, float* workspace, int B, int C, int P, int group, void* stream);
 
-/* L2 normalise rows: y = x / |x| (model_t.py:160). */
-int vlmclip_l2norm_rows(const float* x, float* y, int R, int P, void* stream);
+/* Back-propagate a given dlogits [B,C] through logits = scale * f_img f_txt^T (for callers that apply their own
+ * criterion to the logits, main.py:78-84).  d_img [B,P] and/or d_txt [C,P] are written. */
+int vlmclip_class_head_bwd(const float* f_img, const float* f_txt, const float* dlogits, float scale, float* d_img,
+                           float* d_txt, int B, int C, int P, void* stream);
+
+/* L2 normalise rows: y = s / |s| with s = x (+ x2 if given) (model_t.py:160; model_v.py:306-315 where
+ * normalise((a+b)/2) == normalise(a+b)).  sum_out (optional) receives s for the backward. */
+int vlmclip_l2norm_rows(const float* x, const float* x2, float* y, float* sum_out, int R, int P, void* stream);
 int vlmclip_l2norm_rows_bwd(const float* x, const float* dy, float* dx, int R, int P, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -239,6 +239,25 @@ def contrastive_loss(text_features: Tensor, image_features: Tensor, logit_scale:
     return {"loss": loss, "text_features": t, "image_features": i, "logits_per_text": lpt, "logits_per_image": lpi}
 
 
+def contrastive_loss_local_rows(t_all: Tensor, i_all: Tensor, t_loc: Tensor, i_loc: Tensor, row0: int, logit_scale: Tensor):
+    """Data-parallel statement of the same loss: the global loss with this rank's rows being the
+    differentiable leaves t_loc / i_loc; its gradient is dL_global/d(local rows)."""
+    n = t_loc.shape[0]
+    t = torch.cat([t_all[:row0].detach(), t_loc, t_all[row0 + n:].detach()], 0)
+    i = torch.cat([i_all[:row0].detach(), i_loc, i_all[row0 + n:].detach()], 0)
+    return contrastive_loss(t, i, logit_scale)["loss"]
+
+
+def mhsa_adapter(x: Tensor, a: Dict[str, Tensor], heads: int) -> Tensor:
+    """ContextAdapter / SharedAdapter (adapter/peclip.py:31-34,45-48): LayerNorm(MHSA(x, x, x) + x)."""
+    D = x.shape[-1]
+    qkv = linear(x, a["mhsa.in_proj_weight"], a["mhsa.in_proj_bias"])
+    q, k, v = qkv.split(D, dim=-1)
+    att = attention_core(q, k, v, heads, False, None)
+    y = linear(att, a["mhsa.out_proj.weight"], a["mhsa.out_proj.bias"])
+    return layer_norm(y + x, a["layer_norm.weight"], a["layer_norm.bias"])
+
+
 def model_m_forward(sd, heads_t, heads_v, input_ids, attention_mask, pixel_values, text_adapter, vision_adapter):
     t = model_m_text_features(sd, heads_t, input_ids, attention_mask, text_adapter)
     i = model_m_image_features(sd, heads_v, pixel_values, vision_adapter)

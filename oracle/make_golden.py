@@ -1,0 +1,245 @@
+"""Generates tests/golden/*.pt by EXECUTING THE UNMODIFIED REFERENCE (imported from /root/reference) on seeded
+inputs.  Run in the build container only (the reference does not travel to the GPU box):
+
+    HF_HUB_OFFLINE=1 python oracle/make_golden.py
+
+Shims (monkey-patches in this process; no reference file is touched):
+  1. CLIPModel.from_pretrained -> seeded random-init CLIPModel(CLIPConfig) of the named checkpoint's dims
+     (there are no weights offline); CLIPProcessor.from_pretrained -> a stub object.
+  2. Tracks T/V only: CLIPModel.get_image_features/get_text_features return the pooled tensor (transformers
+     4.51.3 semantics the reference was written for; 5.5.0 returns BaseModelOutputWithPooling).
+  3. Track V only: sys.modules["qwen_vl_utils"] stub; a truthy vlm_context_extractor so no VLM is built.
+
+The fixtures hold inputs' seeds and the reference's outputs (small slices / checksums for big tensors).
+tests/test_oracle.py replays them through oracle/clip_oracle.py; the GPU tests replay them through the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference")
+OUT = ROOT / "tests" / "golden"
+
+from oracle import clip_oracle as O  # noqa: E402
+
+B32 = "openai/clip-vit-base-patch32"
+
+
+def summary(t: torch.Tensor, n: int = 64):
+    t = t.detach().float().reshape(-1)
+    return {"head": t[:n].clone(), "sum": t.double().sum().item(), "abs_sum": t.double().abs().sum().item(),
+            "numel": t.numel()}
+
+
+def install_shims(layers_v=None, layers_t=None):
+    from transformers import CLIPModel, CLIPProcessor
+
+    def fake_from_pretrained(name, *a, **k):
+        return O.build_hf_clip(name, seed=0, vision_layers=layers_v, text_layers=layers_t)
+
+    CLIPModel.from_pretrained = staticmethod(fake_from_pretrained)
+    CLIPProcessor.from_pretrained = staticmethod(lambda name, *a, **k: types.SimpleNamespace(name=name))
+    stub = types.ModuleType("qwen_vl_utils")
+    stub.process_vision_info = lambda *a, **k: (None, None)
+    sys.modules["qwen_vl_utils"] = stub
+    sys.path.insert(0, str(REF))
+
+
+def pooled_tensor_semantics():
+    from transformers import CLIPModel
+
+    gi, gt = CLIPModel.get_image_features, CLIPModel.get_text_features
+
+    def img(self, *a, **k):
+        o = gi(self, *a, **k)
+        return getattr(o, "pooler_output", o)
+
+    def txt(self, *a, **k):
+        o = gt(self, *a, **k)
+        return getattr(o, "pooler_output", o)
+
+    CLIPModel.get_image_features, CLIPModel.get_text_features = img, txt
+
+
+def golden_adapters():
+    """G2: the committed fixture weights through the reference TextAdapter / VisionAdapter, fwd + bwd."""
+    from adapter.clip_adapter import TextAdapter, VisionAdapter
+    from adapter.peclip import ContextAdapter, TextualAdapter
+
+    sd = torch.load(REF / "test_checkpoints" / "test_adapter.pt", map_location="cpu")
+    g = torch.Generator().manual_seed(123)
+    xt = torch.randn(4, 77, 512, generator=g)
+    xv = torch.randn(4, 50, 768, generator=g)
+    ta, va = TextAdapter(512, 256), VisionAdapter(768, 256)
+    ta.load_state_dict(sd["text_adapter"])
+    va.load_state_dict(sd["vision_adapter"])
+    yt, yv = ta(xt), va(xv)
+    loss = yt[:, 0, :].pow(2).mean()
+    loss.backward()
+    out = {
+        "seed": 123,
+        # the text half of the reference's own checkpoint fixture (test_checkpoints/test_adapter.pt), kept in bf16-exact
+        # form is not possible (default-init fp32), so it is stored as is: 1 MB, needed to replay G2 bit for bit
+        "text_adapter": {k: v.clone() for k, v in sd["text_adapter"].items()},
+        "checkpoint_keys": {k: {kk: tuple(vv.shape) for kk, vv in v.items()} for k, v in sd.items()},
+        "y_text_tok0": yt[:, 0, :].detach().clone(), "y_text_abs_sum": yt.detach().double().abs().sum().item(),
+        "y_vision_tok0": yv[:, 0, :].detach().clone(), "y_vision_abs_sum": yv.detach().double().abs().sum().item(),
+        "loss": loss.item(),
+        "grad_down_w": summary(ta.down_project.weight.grad), "grad_up_w": summary(ta.up_project.weight.grad),
+        "grad_ln_w": ta.layer_norm.weight.grad.clone(), "grad_ln_b": ta.layer_norm.bias.grad.clone(),
+        "grad_down_b": ta.down_project.bias.grad.clone(),
+    }
+    # PE-CLIP modules (adapter/peclip.py), default init under a fixed seed
+    torch.manual_seed(7)
+    pe_t = TextualAdapter(768, 256)
+    pe_c = ContextAdapter(1024, 16).eval()
+    g2 = torch.Generator().manual_seed(9)
+    x1 = torch.randn(3, 77, 768, generator=g2)
+    x2 = torch.randn(2, 257, 1024, generator=g2) * 0.5
+    with torch.no_grad():
+        # weights are reproducible from the seed (same construction order as the mirrors): only outputs are stored
+        out["peclip"] = {"seed_modules": 7, "seed_inputs": 9,
+                         "textual_w_head": pe_t.down_proj.weight.reshape(-1)[:16].clone(),
+                         "textual_y_tok0": pe_t(x1)[:, 0, :].clone(),
+                         "context_w_head": pe_c.mhsa.in_proj_weight.reshape(-1)[:16].clone(),
+                         "context_y_rows": pe_c(x2)[:, :4, :].clone(), "context_y_abs_sum": pe_c(x2).double().abs().sum().item()}
+    return out
+
+
+def golden_track_m():
+    """G1: CLIPWithAdapters (ViT-B/32 dims, seeded random init), B=8, .train(): loss/logits/features/adapter grads,
+    then two steps of the reference CLIPAdapterTrainer loop (trainer.py:73-99)."""
+    from model_m import CLIPWithAdapters
+    from trainer import CLIPAdapterTrainer
+
+    torch.manual_seed(1)
+    model = CLIPWithAdapters(use_shared_adapters=False)
+    model.train()
+    pix, ids, mask = O.synthetic_batch(8, seed=2)
+    out = model(input_ids=ids, attention_mask=mask, pixel_values=pix, return_loss=True)
+    out["loss"].backward()
+    n_adapter = sum(p.numel() for n, p in model.named_parameters() if "adapter" in n)
+    n_total = sum(p.numel() for p in model.parameters())
+    res = {
+        "loss": out["loss"].item(), "n_adapter_params": n_adapter, "n_total_params": n_total,
+        "logits_per_text": out["logits_per_text"].detach().clone(),
+        "text_features": out["text_features"].detach().clone(), "image_features": out["image_features"].detach().clone(),
+        "grad_vision_down_w": summary(model.vision_adapter.down_project.weight.grad),
+        "grad_vision_ln_w": model.vision_adapter.layer_norm.weight.grad.clone(),
+        "grad_text_ln_b": model.text_adapter.layer_norm.bias.grad.clone(),
+        "keys": sorted(out.keys()),
+    }
+    # variant with distinct first tokens (DummyDataset-like), so text rows differ
+    ids2 = ids.clone()
+    ids2[:, 0] = torch.arange(8) * 37 + 5
+    model.zero_grad()
+    out2 = model(input_ids=ids2, attention_mask=mask, pixel_values=pix, return_loss=True)
+    res["loss_vary_tok0"] = out2["loss"].item()
+    res["logits_vary_tok0"] = out2["logits_per_text"].detach().clone()
+    out3 = model(input_ids=ids2, attention_mask=mask, pixel_values=pix, return_loss=False)
+    res["unnormalised_text_features"] = out3["text_features"].detach().clone()
+
+    # two optimiser steps through the reference trainer
+    class Loader(list):
+        pass
+
+    batches = Loader()
+    for s in range(2):
+        p, i, m = O.synthetic_batch(8, seed=20 + s)
+        i[:, 0] = torch.randint(0, 1000, (8,), generator=torch.Generator().manual_seed(s))
+        batches.append({"input_ids": i, "attention_mask": m, "pixel_values": p})
+    torch.manual_seed(1)
+    model2 = CLIPWithAdapters(use_shared_adapters=False)
+    tr = CLIPAdapterTrainer(model2, batches, output_dir="/tmp/vlmclip_golden_ckpt", warmup_steps=0)
+    init = {n: p.detach().clone() for n, p in model2.named_parameters() if "adapter" in n}
+    tr.train(num_epochs=1, save_every=10)
+    res["trainer"] = {
+        "update_vision_up_b": (model2.vision_adapter.up_project.bias.detach() - init["vision_adapter.up_project.bias"]).clone(),
+        "update_text_down_b": (model2.text_adapter.down_project.bias.detach() - init["text_adapter.down_project.bias"]).clone(),
+        "update_vision_down_w": summary(model2.vision_adapter.down_project.weight.detach() - init["vision_adapter.down_project.weight"]),
+        "lr": 5e-5, "weight_decay": 0.01, "steps": 2,
+    }
+    return res
+
+
+def golden_track_tv():
+    """Tracks T and V (BASELINE config 1 shape: 8 images x 26 prompts) through the reference classes."""
+    pooled_tensor_semantics()
+    import model_t
+    import model_v
+
+    dev = torch.device("cpu")
+    model_t.device = dev
+    # ---- Track T: build the object without running the processor-dependent __init__ ----
+    t = model_t.CLIPAdapter.__new__(model_t.CLIPAdapter)
+    from transformers import CLIPModel
+
+    t.model = CLIPModel.from_pretrained(B32)
+    for p in t.model.parameters():
+        p.requires_grad = False
+    torch.manual_seed(3)
+    t.visual_adapter = model_t.VisualAdapter(512, 64)
+    t.text_adapter = model_t.TextAdapter(512, 64)
+    t.alpha, t.beta = 0.2, 0.2
+    g = torch.Generator().manual_seed(4)
+    C = 26
+    emb = torch.nn.functional.normalize(torch.randn(C, 512, generator=g), dim=-1)
+    t.emotion_embedding_tensor = emb.clone()
+    t.original_emotion_text_features = {f"c{i}": emb[i:i + 1] for i in range(C)}
+    pix = torch.randn(8, 3, 224, 224, generator=g)
+    labels = torch.randint(0, C, (8,), generator=g)
+    w_head = t.visual_adapter.fc1.weight.reshape(-1)[:16].detach().clone()
+    probs0 = t.predict(pix).clone()
+    t.train([(pix, labels, None)], num_epochs=1, learning_rate=3e-4)
+    probs1 = t.predict(pix).clone()
+    res_t = {"C": C, "seed_adapters": 3, "seed_data": 4, "w_head": w_head, "labels": labels, "probs_before": probs0, "probs_after_1_step": probs1,
+             "visual_fc2_b_after": t.visual_adapter.fc2.bias.detach().clone(),
+             "text_fc1_b_after": t.text_adapter.fc1.bias.detach().clone(),
+             "adapted_embeddings": t.adapted_emotion_embedding_tensor.clone()}
+    # predict_with_all_descriptions: 7 classes x 5 prompts
+    model_t.EMOTIONS = [f"e{i}" for i in range(7)]
+    per = {e: [torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1) for _ in range(5)]
+           for e in model_t.EMOTIONS}
+    t.emotion_text_features_per_description = per
+    res_t["per_prompt"] = torch.cat([torch.cat(v, 0) for v in per.values()], 0)
+    res_t["probs_all_descriptions"] = t.predict_with_all_descriptions(pix).clone()
+
+    # ---- Track V ----
+    v = model_v.EnhancedCLIPAdapter(clip_model_name=B32, bottleneck_dim=192, device="cpu", vlm_context_extractor=object())
+    v.emotion_embedding_tensor = emb.clone()
+    gw = torch.Generator().manual_seed(5)  # reproducible adapter weights (the ctor's RNG state depends on the CLIP build)
+    for mod in (v.visual_adapter, v.text_adapter, v.context_adapter):
+        for prm in mod.parameters():
+            prm.data = torch.randn(prm.shape, generator=gw) * 0.05
+    v.eval()
+    ctx = torch.nn.functional.normalize(torch.randn(8, 512, generator=g), dim=-1)
+    with torch.no_grad():
+        logits_ctx = v(pix, ctx).clone()
+        logits_noctx = v(pix, None).clone()
+    res_v = {"seed_adapters": 5, "adapter_param_order": ["visual", "text", "context"], "ctx": ctx,
+             "alpha": v.alpha, "beta": v.beta, "gamma": v.gamma, "logits_ctx": logits_ctx, "logits_noctx": logits_noctx,
+             "probs": v.predict_probs(pix, ctx).clone()}
+    return {"t": res_t, "v": res_v}
+
+
+def main():
+    os.environ.setdefault("HF_HUB_OFFLINE", "1")
+    torch.set_num_threads(os.cpu_count() or 1)
+    OUT.mkdir(parents=True, exist_ok=True)
+    install_shims()
+    torch.save(golden_adapters(), OUT / "adapters.pt")
+    torch.save(golden_track_m(), OUT / "track_m.pt")
+    torch.save(golden_track_tv(), OUT / "track_tv.pt")
+    for f in sorted(OUT.glob("*.pt")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

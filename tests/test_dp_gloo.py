@@ -1,0 +1,79 @@
+"""World-size-2 `gloo` test of the data-parallel protocol on the CPU: all-gather of the local
+features, global loss on every rank, gradients for local rows only, SUM all-reduce of parameter gradients —
+must reproduce the single-process loss and gradients of the concatenated batch.  The arithmetic here is the
+oracle's (the CUDA kernel's local-row gradient is checked against the same identity on the GPU in
+tests/test_gpu_kernels.py::test_clip_loss_data_parallel_rows)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import clip_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vlm_clip_b200.dist import allreduce_sum_, gather_features
+
+    torch.manual_seed(0)
+    N, P, D = 8, 32, 16
+    nl = N // world
+    x_t, x_i = torch.randn(N, D), torch.randn(N, D)  # identical on every rank (same seed): the global batch
+    W = torch.nn.Parameter(torch.randn(P, D) * 0.3)  # a replicated trainable "adapter"
+    scale = torch.tensor(2.0)
+    # local forward on this rank's shard
+    sl = slice(rank * nl, (rank + 1) * nl)
+    t_loc, i_loc = x_t[sl] @ W.t(), torch.tanh(x_i[sl] @ W.t())
+    t_all, i_all, row0 = gather_features(t_loc, i_loc)
+    assert row0 == rank * nl and t_all.shape == (N, P)
+    loss = O.contrastive_loss_local_rows(t_all, i_all, t_loc, i_loc, row0, scale)
+    loss.backward()
+    flat = W.grad.reshape(-1).clone()
+    allreduce_sum_(flat)
+    # single-process reference on the concatenated batch
+    W2 = torch.nn.Parameter(W.detach().clone())
+    ref = O.contrastive_loss(x_t @ W2.t(), torch.tanh(x_i @ W2.t()), scale)["loss"]
+    ref.backward()
+    q.put((rank, abs(loss.item() - ref.item()), (flat - W2.grad.reshape(-1)).abs().max().item(),
+           W2.grad.abs().max().item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_dp_global_loss_and_summed_grads_match_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, dl, dg, gmax in res:
+        assert dl < 1e-6, (rank, dl)
+        assert dg < 1e-6 * max(1.0, gmax) + 1e-7, (rank, dg, gmax)
+
+
+def test_gather_is_identity_without_process_group():
+    from vlm_clip_b200.dist import allreduce_sum_, gather_features, world
+
+    assert world() == (1, 0)
+    t, i = torch.randn(4, 8), torch.randn(4, 8)
+    ta, ia, r0 = gather_features(t, i)
+    assert r0 == 0 and torch.equal(ta, t) and torch.equal(ia, i)
+    g = torch.ones(3)
+    assert allreduce_sum_(g) is g

@@ -1,0 +1,197 @@
+"""Replays the golden vectors recorded from the EXECUTED reference (tests/golden/*.pt, oracle/make_golden.py) through
+the CUDA path: adapters (G2), PE-CLIP modules, Track-M model (G1), Track-T/V heads and predict paths.  fp32 kernels
+are held to fp32 tolerances; anything behind the bf16 backbone to the bounds of tests/test_gpu_model.py."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+B32 = "openai/clip-vit-base-patch32"
+
+
+@pytest.fixture(scope="module")
+def clip_b32(cuda):
+    m = O.build_hf_clip(B32, seed=0).to(cuda)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m
+
+
+def test_G2_fixture_adapter_forward_backward(cuda):
+    from vlm_clip_b200.adapter.clip_adapter import TextAdapter
+
+    g = torch.load(GOLD / "adapters.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    xt = torch.randn(4, 77, 512, generator=gen).to(cuda)
+    ta = TextAdapter(512, 256)
+    ta.load_state_dict(g["text_adapter"])
+    ta.to(cuda)
+    y = ta(xt)  # all-token module API (adapter/clip_adapter.py:17-23)
+    assert y.shape == (4, 77, 512)
+    assert torch.allclose(y[:, 0, :].cpu(), g["y_text_tok0"], atol=1e-5)
+    assert abs(y.double().abs().sum().item() - g["y_text_abs_sum"]) < 0.05
+    loss = y[:, 0, :].pow(2).mean()
+    loss.backward()
+    assert abs(loss.item() - g["loss"]) < 1e-6
+    assert torch.allclose(ta.layer_norm.weight.grad.cpu(), g["grad_ln_w"], atol=1e-7)
+    assert torch.allclose(ta.layer_norm.bias.grad.cpu(), g["grad_ln_b"], atol=1e-7)
+    assert abs(ta.layer_norm.weight.grad.sum().item() - 1.999981) < 1e-5
+    assert torch.allclose(ta.down_project.bias.grad.cpu(), g["grad_down_b"], atol=1e-8)
+    # token-0 fast path is result-identical to slicing the all-token output
+    y0 = ta.forward_token0(xt.reshape(4 * 77, 512).contiguous(), 4, 77)
+    assert torch.allclose(y0, y[:, 0, :], atol=1e-6)
+
+
+def test_peclip_modules(cuda):
+    from vlm_clip_b200.adapter.peclip import ContextAdapter, TextualAdapter
+
+    g = torch.load(GOLD / "adapters.pt")["peclip"]
+    torch.manual_seed(g["seed_modules"])
+    pe_t = TextualAdapter(768, 256)
+    pe_c = ContextAdapter(1024, 16).eval()
+    assert torch.equal(pe_t.down_proj.weight.reshape(-1)[:16], g["textual_w_head"])
+    assert torch.equal(pe_c.mhsa.in_proj_weight.reshape(-1)[:16], g["context_w_head"])
+    gen = torch.Generator().manual_seed(g["seed_inputs"])
+    x1 = torch.randn(3, 77, 768, generator=gen).to(cuda)
+    x2 = (torch.randn(2, 257, 1024, generator=gen) * 0.5).to(cuda)
+    pe_t.to(cuda)
+    pe_c.to(cuda)
+    y1 = pe_t(x1)
+    assert torch.allclose(y1[:, 0, :].cpu(), g["textual_y_tok0"], atol=1e-5)
+    with torch.no_grad():
+        y2 = pe_c(x2)  # bf16 tensor-core path
+    rel = ((y2[:, :4, :].cpu() - g["context_y_rows"]).norm() / g["context_y_rows"].norm()).item()
+    assert rel < 1e-2, rel
+    assert abs(y2.double().abs().sum().item() / g["context_y_abs_sum"] - 1) < 5e-3
+
+
+def test_G1_track_m_known_answer(cuda, clip_b32):
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+
+    g = torch.load(GOLD / "track_m.pt")
+    _ = O.build_hf_clip(B32, seed=0)  # reproduce the reference ctor's RNG consumption before the adapters
+    torch.manual_seed(1)
+    model = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=False).to(cuda).train()
+    assert sum(p.numel() for n, p in model.named_parameters() if "adapter" in n) == g["n_adapter_params"]
+    assert sum(p.numel() for p in model.parameters()) == g["n_total_params"]
+    pix, ids, mask = O.synthetic_batch(8, seed=2)
+    out = model(input_ids=ids.to(cuda), attention_mask=mask.to(cuda), pixel_values=pix.to(cuda), return_loss=True)
+    assert sorted(out.keys()) == g["keys"]
+    assert abs(out["loss"].item() - g["loss"]) < 4e-3  # known answer 2.0802860 through the bf16 backbone
+    rel = lambda a, b: ((a.cpu() - b).norm() / b.norm()).item()
+    assert rel(out["image_features"], g["image_features"]) < 2e-2
+    assert rel(out["text_features"], g["text_features"]) < 2e-2
+    ids2 = ids.clone()
+    ids2[:, 0] = torch.arange(8) * 37 + 5
+    out2 = model(input_ids=ids2.to(cuda), attention_mask=mask.to(cuda), pixel_values=pix.to(cuda), return_loss=True)
+    assert abs(out2["loss"].item() - g["loss_vary_tok0"]) < 4e-3
+    assert torch.equal(out2["logits_per_text"].argmax(1).cpu(), g["logits_vary_tok0"].argmax(1))
+    out3 = model(input_ids=ids2.to(cuda), attention_mask=mask.to(cuda), pixel_values=pix.to(cuda), return_loss=False)
+    assert rel(out3["text_features"], g["unnormalised_text_features"]) < 2e-2  # un-normalised without the loss
+
+
+def _track_t(cuda, clip_b32, g):
+    from vlm_clip_b200 import model_t
+
+    model_t.device = cuda
+    torch.manual_seed(g["seed_adapters"])
+    t = model_t.CLIPAdapter(B32, clip=clip_b32, encode=False)
+    assert torch.equal(t.visual_adapter.fc1.weight.reshape(-1)[:16].cpu(), g["w_head"])
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    emb = torch.nn.functional.normalize(torch.randn(g["C"], 512, generator=gen), dim=-1)
+    pix = torch.randn(8, 3, 224, 224, generator=gen)
+    labels = torch.randint(0, g["C"], (8,), generator=gen)
+    t.emotion_embedding_tensor = emb.to(cuda)
+    return t, pix.to(cuda), labels.to(cuda)
+
+
+def test_track_t_train_step_and_predict(cuda, clip_b32):
+    g = torch.load(GOLD / "track_tv.pt")["t"]
+    t, pix, labels = _track_t(cuda, clip_b32, g)
+    p0 = t.predict(pix)
+    assert torch.equal(p0.argmax(1).cpu(), g["probs_before"].argmax(1))  # argmax identical
+    # 100x-scaled near-tie softmax: compare the log-probabilities' spread instead of raw probabilities
+    assert (p0.cpu() - g["probs_before"]).abs().max().item() < 0.08
+    t.train([(pix, labels, None)], num_epochs=1, learning_rate=3e-4)  # model_t.py:131-211 with the fused kernels
+    # Adam's first step moves every element by ~lr: compare the signed update of the visual fc2 bias
+    upd = t.visual_adapter.fc2.bias.detach().cpu()
+    ref = g["visual_fc2_b_after"]
+    cos = torch.nn.functional.cosine_similarity((upd - upd.mean()).flatten(), (ref - ref.mean()).flatten(), dim=0)
+    assert torch.allclose(upd, ref, atol=6.5e-4)  # |update| <= 2*lr in the worst (sign-flipped) case
+    assert cos > 0.99
+    assert ((t.adapted_emotion_embedding_tensor.cpu() - g["adapted_embeddings"]).norm() / g["adapted_embeddings"].norm()) < 2e-3
+    p1 = t.predict(pix)
+    assert torch.equal(p1.argmax(1).cpu(), g["probs_after_1_step"].argmax(1))
+    EM = [f"e{i}" for i in range(7)]
+    t.emotion_text_features_per_description = {e: [g["per_prompt"][i * 5 + j:i * 5 + j + 1].to(cuda) for j in range(5)]
+                                               for i, e in enumerate(EM)}
+    pa = t.predict_with_all_descriptions(pix)
+    assert pa.shape == (8, 7)
+    assert torch.equal(pa.argmax(1).cpu(), g["probs_all_descriptions"].argmax(1))
+
+
+def test_track_t_soft_labels_config1(cuda, clip_b32):
+    """BASELINE config 1: 8 images vs 26 EMOTIC prompts with multi-hot soft labels; oracle = F.cross_entropy with
+    probability targets on the oracle's own features."""
+    g = torch.load(GOLD / "track_tv.pt")["t"]
+    t, pix, _ = _track_t(cuda, clip_b32, g)
+    gen = torch.Generator().manual_seed(12)
+    hot = (torch.rand(8, 26, generator=gen) < 0.1).float()
+    hot[torch.arange(8), torch.randint(0, 26, (8,), generator=gen)] = 1.0
+    soft = (hot / hot.sum(1, keepdim=True)).to(cuda)
+    from vlm_clip_b200 import ops
+
+    opt = ops.FusedAdamW(list(t.visual_adapter.parameters()) + list(t.text_adapter.parameters()), lr=3e-4,
+                         weight_decay=0.0, max_grad_norm=0.0)
+    temp = float(t.model.logit_scale.exp())
+    va = {k: v.detach().clone() for k, v in t.visual_adapter.state_dict().items()}
+    ta = {k: v.detach().clone() for k, v in t.text_adapter.state_dict().items()}
+    loss = t.train_step(pix, soft, opt, temp)
+    sd = {k: v.detach() for k, v in clip_b32.state_dict().items()}
+    with torch.no_grad():
+        f = O.hf_pooled_image_features(sd, pix, 12)
+        f = f / f.norm(dim=-1, keepdim=True)
+        ref = O.class_prompt_loss(O.class_prompt_logits(f, t.emotion_embedding_tensor, va, ta, 0.2, 0.2, temp), soft)
+    assert abs(loss.item() - ref.item()) < 5e-3
+
+
+def test_track_v_logits(cuda, clip_b32):
+    from vlm_clip_b200 import model_v
+
+    g = torch.load(GOLD / "track_tv.pt")
+    gt, gv = g["t"], g["v"]
+    gen = torch.Generator().manual_seed(gt["seed_data"])
+    emb = torch.nn.functional.normalize(torch.randn(gt["C"], 512, generator=gen), dim=-1)
+    pix = torch.randn(8, 3, 224, 224, generator=gen)
+    v = model_v.EnhancedCLIPAdapter(clip=clip_b32, bottleneck_dim=192, device=cuda, vlm_context_extractor=object())
+    gw = torch.Generator().manual_seed(gv["seed_adapters"])
+    for mod in (v.visual_adapter, v.text_adapter, v.context_adapter):
+        for prm in mod.parameters():
+            prm.data = (torch.randn(prm.shape, generator=gw) * 0.05).to(cuda)
+    v.emotion_embedding_tensor = emb.to(cuda)
+    v.eval()
+    with torch.no_grad():
+        l_ctx = v(pix.to(cuda), gv["ctx"].to(cuda))
+        l_no = v(pix.to(cuda), None)
+        probs = v.predict_probs(pix.to(cuda), gv["ctx"].to(cuda))
+    # logits are 14.3 * cosines of unit vectors: absolute error is the meaningful measure
+    assert (l_ctx.cpu() - gv["logits_ctx"]).abs().max().item() < 0.05
+    assert (l_no.cpu() - gv["logits_noctx"]).abs().max().item() < 0.05
+    assert torch.equal(probs.argmax(1).cpu(), gv["probs"].argmax(1))
+    # differentiable logits + torch criterion, the loop of main.py:78-84
+    v.train()
+    for mod in (v.visual_adapter, v.text_adapter, v.context_adapter):
+        mod.dropout.p = 0.0
+    labels = torch.randint(0, gt["C"], (8,), generator=gen).to(cuda)
+    logits = v(pix.to(cuda), gv["ctx"].to(cuda))
+    torch.nn.CrossEntropyLoss()(logits, labels).backward()
+    loss2, _ = v.loss(pix.to(cuda), labels, gv["ctx"].to(cuda))
+    g1 = v.context_adapter.fc1.weight.grad.clone()
+    for prm in v.get_trainable_parameters():
+        prm.grad = None
+    loss2.backward()
+    assert torch.allclose(v.context_adapter.fc1.weight.grad, g1, atol=1e-6, rtol=1e-4)

@@ -42,7 +42,8 @@ PROTOTYPES = {
     "vlmclip_clip_loss_workspace": (_i64, [_i, _i]),
     "vlmclip_clip_loss": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_class_head": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "vlmclip_l2norm_rows": (_i, [_p, _p, _i, _i, _p]),
+    "vlmclip_class_head_bwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _p]),
+    "vlmclip_l2norm_rows": (_i, [_p, _p, _p, _p, _i, _i, _p]),
     "vlmclip_l2norm_rows_bwd": (_i, [_p, _p, _p, _i, _i, _p]),
     "vlmclip_adamw_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vlmclip_gather_rows_bf16_to_f32": (_i, [_p, _i64, _p, _i, _i, _p]),

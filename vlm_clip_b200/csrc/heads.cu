@@ -18,16 +18,27 @@ void count_launch(int n);
 namespace {
 
 // ---------------------------------------------------------------- L2 normalise
+// y = s / |s|, s = x (+ x2): the optional second operand is the context branch of model_v.py:306-315, where
+// normalise((a + b) / 2) == normalise(a + b).  sum_out (optional) keeps s for the backward.
 __global__ void __launch_bounds__(256)
-l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_out, int R, int P) {
+l2norm_rows_kernel(const float* __restrict__ x, const float* __restrict__ x2, float* __restrict__ y,
+                   float* __restrict__ inv_out, float* __restrict__ sum_out, int R, int P) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + (int64_t)row * P;
+  const float* x2r = x2 != nullptr ? x2 + (int64_t)row * P : nullptr;
   float q = 0.f;
-  for (int c = lane; c < P; c += 32) q = fmaf(xr[c], xr[c], q);
+  for (int c = lane; c < P; c += 32) {
+    const float v = xr[c] + (x2r != nullptr ? x2r[c] : 0.f);
+    q = fmaf(v, v, q);
+  }
   const float inv = 1.f / sqrtf(warp_sum(q));
-  for (int c = lane; c < P; c += 32) y[(int64_t)row * P + c] = xr[c] * inv;
+  for (int c = lane; c < P; c += 32) {
+    const float v = xr[c] + (x2r != nullptr ? x2r[c] : 0.f);
+    y[(int64_t)row * P + c] = v * inv;
+    if (sum_out != nullptr) sum_out[(int64_t)row * P + c] = v;
+  }
   if (inv_out != nullptr && lane == 0) inv_out[row] = inv;
 }
 
@@ -324,10 +335,11 @@ class_head_grad_kernel(const float* __restrict__ f_img, const float* __restrict_
 
 using namespace vlmclip;
 
-extern "C" int vlmclip_l2norm_rows(const float* x, float* y, int R, int P, void* stream) {
+extern "C" int vlmclip_l2norm_rows(const float* x, const float* x2, float* y, float* sum_out, int R, int P,
+                                   void* stream) {
   VLMCLIP_CHECK_ARG(x && y && R > 0 && P > 0, "l2norm_rows: bad arguments");
   count_launch(1);
-  l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, y, nullptr, R, P);
+  l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, x2, y, nullptr, sum_out, R, P);
   return report_cuda(cudaGetLastError(), "l2norm_rows_kernel launch");
 }
 
@@ -362,8 +374,8 @@ extern "C" int vlmclip_clip_loss(const float* txt, const float* img, float logit
   float* din = dtn + (int64_t)N * P;
   const int tiles_n = (N + TF_TILE - 1) / TF_TILE;
   count_launch(6);
-  l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(txt, txt_n, inv_t, N, P);
-  l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(img, img_n, inv_i, N, P);
+  l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(txt, nullptr, txt_n, inv_t, nullptr, N, P);
+  l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(img, nullptr, img_n, inv_i, nullptr, N, P);
   VLMCLIP_CUDA(cudaGetLastError());
   sim_logits_kernel<<<dim3(tiles_n, tiles_n), 256, 0, s>>>(txt_n, img_n, Z, logit_scale_exp, N, P);
   row_lse_kernel<<<(N + 7) / 8, 256, 0, s>>>(Z, lse_r, N);
@@ -412,4 +424,17 @@ extern "C" int vlmclip_class_head(const float* f_img, const float* f_txt, float 
                                                 want_grad ? d_txt : nullptr, loss, B, C, P);
   }
   return report_cuda(cudaGetLastError(), "class_head launch");
+}
+
+extern "C" int vlmclip_class_head_bwd(const float* f_img, const float* f_txt, const float* dlogits, float scale,
+                                      float* d_img, float* d_txt, int B, int C, int P, void* stream) {
+  VLMCLIP_CHECK_ARG(f_img && f_txt && dlogits && (d_img || d_txt), "class_head_bwd: null pointer");
+  VLMCLIP_CHECK_ARG(B > 0 && C > 0 && P > 0, "class_head_bwd: bad dims");
+  const int64_t total = (int64_t)(B + C) * P;
+  int grid = (int)((total + 255) / 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  count_launch(1);
+  class_head_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(f_img, f_txt, dlogits, nullptr, scale, d_img, d_txt,
+                                                                 nullptr, B, C, P);
+  return report_cuda(cudaGetLastError(), "class_head_bwd launch");
 }

@@ -11,7 +11,7 @@ void count_launch(int n);
 namespace {
 
 constexpr int ROWS_PER_BLOCK = 8;
-constexpr int MAX_VEC = 8;  // 8 x (32 lanes x 8 elements) = D <= 2048
+constexpr int MAX_VEC = 8;  // 8 x (32 lanes x 8 elements) = D <= 2048 (kernels are instantiated for 2,3,4,8)
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   f[0] = bf16_lo(q.x);
@@ -32,12 +32,13 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return o;
 }
 
-// mean / rstd of one row held as v[nv][8] per lane
-__device__ __forceinline__ void row_mean_rstd(float (*v)[8], int nvec_lane_valid[MAX_VEC], int D, float eps,
-                                              float& mean, float& rstd) {
+// mean / rstd of one row held as v[NV][8] per lane
+template <int NV>
+__device__ __forceinline__ void row_mean_rstd(float (*v)[8], int* nvec_lane_valid, int D, float eps, float& mean,
+                                              float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
+  for (int i = 0; i < NV; ++i)
     if (nvec_lane_valid[i])
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -45,7 +46,7 @@ __device__ __forceinline__ void row_mean_rstd(float (*v)[8], int nvec_lane_valid
   mean = s / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i)
+  for (int i = 0; i < NV; ++i)
     if (nvec_lane_valid[i])
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void row_mean_rstd(float (*v)[8], int nvec_lane_valid
 }
 
 // MODE 0: y = LN(x) bf16 (+stats)   MODE 1: stats only   MODE 2: y = LN(x) written as fp32
-template <int MODE>
+template <int MODE, int NV>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, void* __restrict__ y_, int64_t ldy,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ stats, int M,
@@ -66,11 +67,11 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, void* __restr
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  float v[MAX_VEC][8];
-  int valid[MAX_VEC];
+  float v[NV][8];
+  int valid[NV];
   const __nv_bfloat16* xr = x + (int64_t)row * ldx;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     valid[i] = vi < nvec;
     if (valid[i]) {
@@ -79,7 +80,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, void* __restr
     }
   }
   float mean, rstd;
-  row_mean_rstd(v, valid, D, eps, mean, rstd);
+  row_mean_rstd<NV>(v, valid, D, eps, mean, rstd);
   if (stats != nullptr && lane == 0) {
     stats[2 * (int64_t)row] = mean;
     stats[2 * (int64_t)row + 1] = rstd;
@@ -88,7 +89,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, void* __restr
     __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(y_) + (int64_t)row * ldy;
     float* yf = reinterpret_cast<float*>(y_) + (int64_t)row * ldy;
 #pragma unroll
-    for (int i = 0; i < MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (valid[i]) {
         const int c = (lane + i * 32) * 8;
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -145,7 +146,56 @@ im2col_kernel(const PixT* __restrict__ pix, __nv_bfloat16* __restrict__ out, int
   }
 }
 
+// Fast path for patch % 8 == 0: one thread moves 8 horizontally adjacent pixels.  Threads are ordered along
+// image rows, so global reads are fully coalesced; every write is one full 16-byte bf16 vector.
+template <typename PixT>
+__global__ void __launch_bounds__(256)
+im2col_rows_kernel(const PixT* __restrict__ pix, __nv_bfloat16* __restrict__ out, int B, int H, int W, int p,
+                   int Kpad) {
+  const int w8 = W >> 3;
+  const int gw = W / p, gh = H / p;
+  const int64_t total = (int64_t)B * 3 * H * w8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x8 = (int)(idx % w8);
+    int64_t t = idx / w8;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % 3);
+    const int b = (int)(t / 3);
+    const int x = x8 * 8;
+    const PixT* src = pix + (((int64_t)b * 3 + c) * H + y) * W + x;
+    float f[8];
+    if (sizeof(PixT) == 4) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w;
+      f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
+    } else {
+      const uint4 q = ld_nc_v4(src);
+      unpack8(q, f);
+    }
+    const int py = y / p, i = y - py * p;
+    const int px = x / p, j = x - px * p;
+    const int64_t m = ((int64_t)b * gh + py) * gw + px;
+    st_v4(out + m * Kpad + (c * p * p + i * p + j), pack8(f));
+  }
+}
+
+// zero the padding columns [K, Kpad) (only needed when 3*p*p is not a multiple of 64)
+__global__ void __launch_bounds__(256)
+im2col_pad_kernel(__nv_bfloat16* __restrict__ out, int64_t rows, int K, int Kpad) {
+  const int padw = Kpad - K;
+  const int64_t total = rows * padw;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / padw;
+    out[r * Kpad + K + (idx - r * padw)] = __float2bfloat16(0.f);
+  }
+}
+
 // vision tokens: x[b,0] = cls + pos[0]; x[b,1+q] = patch[b,q] + pos[1+q]; y = LN(x)
+template <int NV>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                        const float* __restrict__ pos, const float* __restrict__ gamma,
@@ -159,10 +209,10 @@ vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict_
   const int nvec = D >> 3;
   const float* src = (s == 0) ? cls : patch + (b * (S - 1) + (s - 1)) * (int64_t)D;
   const float* pr = pos + (int64_t)s * D;
-  float v[MAX_VEC][8];
-  int valid[MAX_VEC];
+  float v[NV][8];
+  int valid[NV];
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     valid[i] = vi < nvec;
     if (valid[i]) {
@@ -181,10 +231,10 @@ vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict_
     }
   }
   float mean, rstd;
-  row_mean_rstd(v, valid, D, eps, mean, rstd);
+  row_mean_rstd<NV>(v, valid, D, eps, mean, rstd);
   __nv_bfloat16* yr = y + row * D;
 #pragma unroll
-  for (int i = 0; i < MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (valid[i]) {
       const int c = (lane + i * 32) * 8;
       float o[8];
@@ -226,9 +276,28 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __re
   }
 }
 
+// instantiate the row kernels for the per-lane vector counts that occur (D = 512, 768, 1024, <= 2048)
+#define VLMCLIP_DISPATCH_NV(D, CALL)          \
+  do {                                        \
+    const int _nv = ((D) + 255) / 256;        \
+    if (_nv <= 2) {                           \
+      constexpr int NV = 2;                   \
+      CALL;                                   \
+    } else if (_nv == 3) {                    \
+      constexpr int NV = 3;                   \
+      CALL;                                   \
+    } else if (_nv == 4) {                    \
+      constexpr int NV = 4;                   \
+      CALL;                                   \
+    } else {                                  \
+      constexpr int NV = 8;                   \
+      CALL;                                   \
+    }                                         \
+  } while (0)
+
 int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
-  const int64_t cap = (int64_t)sm_count() * 16;
+  const int64_t cap = (int64_t)sm_count() * 32;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
@@ -248,8 +317,8 @@ extern "C" int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64
                     "layernorm: pointers must be 16-byte aligned");
   const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   count_launch(1);
-  layernorm_kernel<0><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, stats_out, M, D, eps);
+  VLMCLIP_DISPATCH_NV(D, (layernorm_kernel<0, NV><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                             (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, stats_out, M, D, eps)));
   return report_cuda(cudaGetLastError(), "layernorm_kernel launch");
 }
 
@@ -264,8 +333,8 @@ extern "C" int vlmclip_layernorm_bf16_f32out(const void* x, int64_t ldx, float* 
                     "layernorm_f32out: pointers must be 16-byte aligned");
   const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   count_launch(1);
-  layernorm_kernel<2><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, nullptr, M, D, eps);
+  VLMCLIP_DISPATCH_NV(D, (layernorm_kernel<2, NV><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                             (const __nv_bfloat16*)x, ldx, y, ldy, gamma, beta, nullptr, M, D, eps)));
   return report_cuda(cudaGetLastError(), "layernorm_kernel<f32out> launch");
 }
 
@@ -277,8 +346,8 @@ extern "C" int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_o
   VLMCLIP_CHECK_ARG(ldx % 8 == 0 && ldx >= D && (uintptr_t)x % 16 == 0, "row_stats: bad ldx/alignment");
   const int grid = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   count_launch(1);
-  layernorm_kernel<1><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, stats_out, M, D, eps);
+  VLMCLIP_DISPATCH_NV(D, (layernorm_kernel<1, NV><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                             (const __nv_bfloat16*)x, ldx, nullptr, 0, nullptr, nullptr, stats_out, M, D, eps)));
   return report_cuda(cudaGetLastError(), "row_stats kernel launch");
 }
 
@@ -290,6 +359,23 @@ extern "C" int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* ou
   const int K = 3 * patch * patch;
   const int Kpad = (K + 63) / 64 * 64;
   VLMCLIP_CHECK_ARG((uintptr_t)out % 16 == 0, "im2col: out must be 16-byte aligned");
+  if (patch % 8 == 0 && W % 8 == 0 && (uintptr_t)pixels % 16 == 0) {
+    const int64_t rows = (int64_t)B * (H / patch) * (W / patch);
+    const int64_t total8 = (int64_t)B * 3 * H * (W / 8);
+    count_launch(1);
+    if (pix_bf16)
+      im2col_rows_kernel<__nv_bfloat16><<<grid_for(total8, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)pixels, (__nv_bfloat16*)out, B, H, W, patch, Kpad);
+    else
+      im2col_rows_kernel<float><<<grid_for(total8, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const float*)pixels, (__nv_bfloat16*)out, B, H, W, patch, Kpad);
+    if (Kpad != K) {
+      count_launch(1);
+      im2col_pad_kernel<<<grid_for(rows * (Kpad - K), 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, rows,
+                                                                                          K, Kpad);
+    }
+    return report_cuda(cudaGetLastError(), "im2col_rows_kernel launch");
+  }
   const int64_t total = (int64_t)B * (H / patch) * (W / patch) * (Kpad / 8);
   count_launch(1);
   if (pix_bf16)
@@ -312,8 +398,8 @@ extern "C" int vlmclip_vision_embed_ln(const float* patch, const float* cls, con
   const int64_t rows = (int64_t)B * S;
   const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   count_launch(1);
-  vision_embed_ln_kernel<<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-      patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps);
+  VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                             patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
   return report_cuda(cudaGetLastError(), "vision_embed_ln_kernel launch");
 }
 

@@ -169,18 +169,10 @@ class CLIPWithAdapters(nn.Module):
             txt_all = img_all = None
             row0 = 0
             if self._dp_enabled:
-                import torch.distributed as dist
+                from .dist import gather_features, world
 
-                if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._dp_group) > 1:
-                    ws = dist.get_world_size(self._dp_group)
-                    rank = dist.get_rank(self._dp_group)
-                    B, P = text_features.shape
-                    both = torch.cat([text_features.detach(), image_features.detach()], dim=1).contiguous()
-                    gathered = torch.empty((ws * B, 2 * P), device=both.device, dtype=both.dtype)
-                    dist.all_gather_into_tensor(gathered, both, group=self._dp_group)
-                    txt_all = gathered[:, :P].contiguous()
-                    img_all = gathered[:, P:].contiguous()
-                    row0 = rank * B
+                if world(self._dp_group)[0] > 1:
+                    txt_all, img_all, row0 = gather_features(text_features, image_features, self._dp_group)
             loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0)
             return {
                 "loss": loss,

@@ -12,6 +12,10 @@ from . import _native as N
 bf16 = torch.bfloat16
 f32 = torch.float32
 
+# bench.py sets this to {"gemm": []} for ONE instrumented step: every dense-layer launch is then bracketed by
+# CUDA events on the launching stream and recorded as (start, stop, algorithmic FLOPs).
+PROFILE = None
+
 
 def _req(cond: bool, msg: str) -> None:
     if not cond:
@@ -33,12 +37,19 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
     if residual is not None:
         _req(residual.dtype == bf16 and residual.shape == (M, Nn) and residual.stride(1) == 1, "gemm: bad residual")
     lib = N.load()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     N.check(
         lib.vlmclip_gemm_bf16(
             N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(out), out.stride(0), N.ptr(bias), N.ptr(residual),
             residual.stride(0) if residual is not None else 0, N.ptr(row_stats), N.ptr(col_c), M, Nn, K, int(act),
             1 if out_fp32 else 0, N.stream()),
         "vlmclip_gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof["gemm"].append((e0, e1, 2.0 * M * Nn * K))
     return out
 
 
@@ -231,27 +242,71 @@ def linear_f32(x, W, b=None):
 
 
 class _L2NormFn(torch.autograd.Function):
+    """y = s/|s|, s = x (+ x2)."""
+
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, x2):
         R, P = x.shape
         y = torch.empty_like(x)
-        N.check(N.load().vlmclip_l2norm_rows(N.ptr(x), N.ptr(y), R, P, N.stream()), "vlmclip_l2norm_rows")
-        ctx.save_for_backward(x)
+        s = torch.empty_like(x) if x2 is not None else None
+        N.check(N.load().vlmclip_l2norm_rows(N.ptr(x), N.ptr(x2), N.ptr(y), N.ptr(s), R, P, N.stream()),
+                "vlmclip_l2norm_rows")
+        ctx.save_for_backward(x if s is None else s)
+        ctx.two = x2 is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        R, P = x.shape
-        dx = torch.empty_like(x)
-        N.check(N.load().vlmclip_l2norm_rows_bwd(N.ptr(x), N.ptr(dy.contiguous()), N.ptr(dx), R, P, N.stream()),
+        (s,) = ctx.saved_tensors
+        R, P = s.shape
+        dx = torch.empty_like(s)
+        N.check(N.load().vlmclip_l2norm_rows_bwd(N.ptr(s), N.ptr(dy.contiguous()), N.ptr(dx), R, P, N.stream()),
                 "vlmclip_l2norm_rows_bwd")
-        return dx
+        return dx, (dx if ctx.two else None)
 
 
-def l2norm(x):
+def l2norm(x, x2=None):
+    """x / |x|, or (x + x2) / |x + x2| (average fusion followed by re-normalisation, model_v.py:306-315)."""
     _req(x.dtype == f32 and x.dim() == 2 and x.is_contiguous(), "l2norm: x must be contiguous fp32 [R, P]")
-    return _L2NormFn.apply(x)
+    if x2 is not None:
+        _req(x2.dtype == f32 and x2.shape == x.shape and x2.is_contiguous(), "l2norm: x2 must match x")
+    return _L2NormFn.apply(x, x2)
+
+
+class _ScaledSimFn(torch.autograd.Function):
+    """logits[B,C] = scale * f_img f_txt^T, differentiable (for callers applying their own criterion)."""
+
+    @staticmethod
+    def forward(ctx, f_img, f_txt, scale):
+        B, P = f_img.shape
+        Cc = f_txt.shape[0]
+        logits = torch.empty((B, Cc), device=f_img.device, dtype=f32)
+        N.check(
+            N.load().vlmclip_class_head(N.ptr(f_img), N.ptr(f_txt), float(scale), None, None, N.ptr(logits), None, None,
+                                        None, None, None, B, Cc, P, 1, N.stream()), "vlmclip_class_head")
+        ctx.save_for_backward(f_img, f_txt)
+        ctx.scale = float(scale)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        f_img, f_txt = ctx.saved_tensors
+        B, P = f_img.shape
+        Cc = f_txt.shape[0]
+        d_img = torch.empty_like(f_img) if ctx.needs_input_grad[0] else None
+        d_txt = torch.empty_like(f_txt) if ctx.needs_input_grad[1] else None
+        if d_img is not None or d_txt is not None:
+            N.check(
+                N.load().vlmclip_class_head_bwd(N.ptr(f_img), N.ptr(f_txt), N.ptr(dlogits.contiguous()), ctx.scale,
+                                                N.ptr(d_img), N.ptr(d_txt), B, Cc, P, N.stream()),
+                "vlmclip_class_head_bwd")
+        return d_img, d_txt, None
+
+
+def scaled_similarity(f_img, f_txt, scale: float):
+    for t in (f_img, f_txt):
+        _req(t.dtype == f32 and t.dim() == 2 and t.is_contiguous(), "scaled_similarity: features must be contiguous fp32")
+    return _ScaledSimFn.apply(f_img, f_txt, float(scale))
 
 
 # --------------------------------------------------------------------------------------------- heads

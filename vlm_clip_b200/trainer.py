@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn  # noqa: F401  (kept for parity with the reference module's namespace)
 
 from . import ops
+from .dist import allreduce_sum_
 from .model_m import CLIPWithAdapters  # noqa: F401
 
 
@@ -99,9 +100,7 @@ class CLIPAdapterTrainer:
         opt = self.optimizer
         opt.zero_grad()
         loss.backward()
-        dist, world, _ = _dist_world()
-        if world > 1:
-            dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM)
+        allreduce_sum_(opt.grad)  # no-op in a single process
         opt.step()
         self._global_step += 1
         if self._total_steps is not None:
