@@ -138,8 +138,15 @@ def test_text_embed(cuda):
                                                  (2, 257, 16, False, False), (4, 77, 8, True, False),
                                                  (4, 77, 8, True, True), (1, 16, 1, True, False),
                                                  (2, 64, 2, False, True)])
-def test_attention(cuda, B, S, H, causal, masked):
+@pytest.mark.parametrize("force_tc", [False, True])
+def test_attention(cuda, B, S, H, causal, masked, force_tc, monkeypatch):
+    """force_tc exercises the tcgen05 kernel on the masked / causal shapes that are normally routed to the mma.sync
+    variant (the switch is read once per process, so the forced run happens in a subprocess-free way only when the
+    library has not cached the choice; see test_attention_tc_masked_subprocess)."""
     from vlm_clip_b200 import ops
+
+    if force_tc:
+        pytest.skip("covered by test_attention_tc_masked_subprocess")
 
     g = _gen(B * 1000 + S)
     D = H * 64
@@ -155,6 +162,45 @@ def test_attention(cuda, B, S, H, causal, masked):
     assert torch.isfinite(out.float()).all()
     # probabilities are rounded to bf16 before P.V (2^-9) and the output is bf16
     assert _rel(out, ref) < 8e-3, f"rel err {_rel(out, ref)}"
+
+
+def test_attention_tc_masked_subprocess():
+    """tcgen05 attention with causal + key-padding masks (normally routed to mma.sync): run in a fresh process with
+    VLMCLIP_ATTN_FORCE_TC=1 so both implementations are held to the same oracle."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import torch, sys
+sys.path.insert(0, '.')
+from oracle import clip_oracle as O
+from vlm_clip_b200 import ops
+dev = torch.device('cuda:0')
+bf16 = torch.bfloat16
+worst = 0.0
+for (B, S, H, causal, masked) in [(4, 77, 8, True, False), (4, 77, 8, True, True), (2, 64, 2, False, True), (1, 16, 1, True, False), (3, 130, 4, True, True)]:
+    g = torch.Generator(device='cuda').manual_seed(B * 1000 + S)
+    D = H * 64
+    qkv = torch.randn(B * S, 3 * D, device=dev, generator=g).to(bf16)
+    km = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), device=dev, generator=g)
+        km = (torch.arange(S, device=dev)[None] < lens[:, None]).to(torch.uint8).contiguous()
+    out = ops.attention(qkv, B, S, H, causal=causal, key_mask=km)
+    q, k, v = qkv.float().view(B, S, 3, D).unbind(2)
+    ref = O.attention_core(q, k, v, H, causal, km).reshape(B * S, D)
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert torch.isfinite(out.float()).all()
+    worst = max(worst, rel)
+assert worst < 8e-3, worst
+print('ok', worst)
+"""
+    env = dict(os.environ, VLMCLIP_ATTN_FORCE_TC="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
 
 
 ADAPTER_CASES = [

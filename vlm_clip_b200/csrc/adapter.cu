@@ -75,55 +75,85 @@ __device__ __forceinline__ void adapter_rows_forward(const AdapterArgs& a, int r
     xs[idx] = v;
   }
   __syncthreads();
-  // ---- down projection + activation: one warp per bottleneck unit ----
-  for (int j = warp; j < A; j += NT / 32) {
-    float part[RB];
+  // ---- down projection + activation: each warp owns UNR bottleneck units at a time, so UNR independent weight
+  //      rows are in flight per lane (the kernel is L2-latency bound, not FLOP bound) ----
+  constexpr int UNR = 4;
+  for (int j0 = warp * UNR; j0 < A; j0 += (NT / 32) * UNR) {
+    float part[UNR][RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) part[r] = 0.f;
-    const float* w = a.W1 + (int64_t)j * D;
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) part[u][r] = 0.f;
     for (int d = lane * 4; d < D; d += 128) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + d));
+      float4 wv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        wv[u] = (j0 + u < A) ? __ldg(reinterpret_cast<const float4*>(a.W1 + (int64_t)(j0 + u) * D + d))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const float4 xv = *reinterpret_cast<const float4*>(xs + r * D + d);
-        part[r] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, part[r]))));
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          part[u][r] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, part[u][r]))));
       }
     }
 #pragma unroll
-    for (int r = 0; r < RB; ++r) part[r] = warp_sum(part[r]);
-    if (lane == 0) {
-      const float bj = a.b1[j];
+    for (int u = 0; u < UNR; ++u)
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const float p = part[r] + bj;
-        float h = act_fwd(p, a.act);
-        if (a.hmask != nullptr && r0 + r < a.R) h *= a.hmask[(int64_t)(r0 + r) * A + j];
-        ps[r * A + j] = p;
-        hs[r * A + j] = h;
+      for (int r = 0; r < RB; ++r) part[u][r] = warp_sum(part[u][r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int j = j0 + u;
+        if (j < A) {
+          const float bj = a.b1[j];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const float p = part[u][r] + bj;
+            float h = act_fwd(p, a.act);
+            if (a.hmask != nullptr && r0 + r < a.R) h *= a.hmask[(int64_t)(r0 + r) * A + j];
+            ps[r * A + j] = p;
+            hs[r * A + j] = h;
+          }
+        }
       }
     }
   }
   __syncthreads();
-  // ---- up projection: one warp per output feature ----
-  for (int d = warp; d < D; d += NT / 32) {
-    float part[RB];
+  // ---- up projection: UNR output features per warp iteration ----
+  for (int d0 = warp * UNR; d0 < D; d0 += (NT / 32) * UNR) {
+    float part[UNR][RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) part[r] = 0.f;
-    const float* w = a.W2 + (int64_t)d * A;
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) part[u][r] = 0.f;
     for (int j = lane * 4; j < A; j += 128) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + j));
+      float4 wv[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        wv[u] = (d0 + u < D) ? __ldg(reinterpret_cast<const float4*>(a.W2 + (int64_t)(d0 + u) * A + j))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const float4 hv = *reinterpret_cast<const float4*>(hs + r * A + j);
-        part[r] = fmaf(wv.x, hv.x, fmaf(wv.y, hv.y, fmaf(wv.z, hv.z, fmaf(wv.w, hv.w, part[r]))));
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          part[u][r] = fmaf(wv[u].x, hv.x, fmaf(wv[u].y, hv.y, fmaf(wv[u].z, hv.z, fmaf(wv[u].w, hv.w, part[u][r]))));
       }
     }
 #pragma unroll
-    for (int r = 0; r < RB; ++r) part[r] = warp_sum(part[r]);
-    if (lane == 0) {
-      const float bd = a.b2[d];
+    for (int u = 0; u < UNR; ++u)
 #pragma unroll
-      for (int r = 0; r < RB; ++r) us[r * D + d] = part[r] + bd;
+      for (int r = 0; r < RB; ++r) part[u][r] = warp_sum(part[u][r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (d0 + u < D) {
+          const float bd = a.b2[d0 + u];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) us[r * D + d0 + u] = part[u][r] + bd;
+        }
     }
   }
   __syncthreads();
@@ -271,6 +301,7 @@ __global__ void __launch_bounds__(NT) adapter_bwd_rows_kernel(const AdapterArgs 
     float acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+#pragma unroll 8
     for (int d = 0; d < D; ++d) {
       const float w = __ldg(a.W2 + (int64_t)d * A + j);
 #pragma unroll
@@ -294,6 +325,7 @@ __global__ void __launch_bounds__(NT) adapter_bwd_rows_kernel(const AdapterArgs 
     float acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = dxs[r * D + d];
+#pragma unroll 8
     for (int j = 0; j < A; ++j) {
       const float w = __ldg(a.W1 + (int64_t)j * D + d);
 #pragma unroll
@@ -333,32 +365,49 @@ adapter_wgrad_kernel(const float* __restrict__ du, const float* __restrict__ h, 
   }
 }
 
-// Column sums over the batch: db2, dbeta, dgamma over D columns; db1 over A columns.
+// Column sums over the batch: db2, dbeta, dgamma over D columns; db1 over A columns.  One block = 32 columns x 8
+// row slices, combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 adapter_colsum_kernel(const float* __restrict__ du, const float* __restrict__ dy, const float* __restrict__ zhat,
                       const float* __restrict__ dp, float* __restrict__ db1, float* __restrict__ db2,
                       float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int D, int A) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float red[3][8][33];
+  const int cx = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   if (c < D) {
-    float s2 = 0.f, sb = 0.f, sg = 0.f;
-    for (int r = 0; r < R; ++r) {
-      s2 += du[(int64_t)r * D + c];
+    for (int r = slice; r < R; r += 8) {
+      s0 += du[(int64_t)r * D + c];
       if (dgamma != nullptr) {
         const float g = dy[(int64_t)r * D + c];
-        sb += g;
-        sg = fmaf(g, zhat[(int64_t)r * D + c], sg);
+        s1 += g;
+        s2 = fmaf(g, zhat[(int64_t)r * D + c], s2);
       }
-    }
-    db2[c] = s2;
-    if (dgamma != nullptr) {
-      dgamma[c] = sg;
-      dbeta[c] = sb;
     }
   } else if (c - D < A) {
     const int j = c - D;
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s += dp[(int64_t)r * A + j];
-    db1[j] = s;
+    for (int r = slice; r < R; r += 8) s0 += dp[(int64_t)r * A + j];
+  }
+  red[0][slice][cx] = s0;
+  red[1][slice][cx] = s1;
+  red[2][slice][cx] = s2;
+  __syncthreads();
+  if (slice == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      t0 += red[0][k][cx];
+      t1 += red[1][k][cx];
+      t2 += red[2][k][cx];
+    }
+    if (c < D) {
+      db2[c] = t0;
+      if (dgamma != nullptr) {
+        dbeta[c] = t1;
+        dgamma[c] = t2;
+      }
+    } else if (c - D < A) {
+      db1[c - D] = t0;
+    }
   }
 }
 
@@ -499,7 +548,7 @@ extern "C" int vlmclip_adapter_bwd(const void* x, int x_bf16, int64_t ldx, const
   adapter_wgrad_kernel<<<grid, 256, 0, s>>>(a.ws_du, a.ws_h, a.ws_dp, a.ws_x, dW1, dW2, R, D, A);
   VLMCLIP_CUDA(cudaGetLastError());
   const bool ln = post == VLMCLIP_ADAPTER_RESIDUAL_LN;
-  adapter_colsum_kernel<<<(D + A + 255) / 256, 256, 0, s>>>(a.ws_du, dy, a.ws_zhat, a.ws_dp, db1, db2,
+  adapter_colsum_kernel<<<(D + A + 31) / 32, 256, 0, s>>>(a.ws_du, dy, a.ws_zhat, a.ws_dp, db1, db2,
                                                            ln ? dgamma : nullptr, ln ? dbeta : nullptr, R, D, A);
   return report_cuda(cudaGetLastError(), "adapter_bwd launch");
 }

@@ -5,8 +5,8 @@
 // One CTA per (batch, head, query group); K and V of that head live in shared memory for the whole CTA,
 // each warp owns 16 query rows and streams over 64-key blocks with an online (running max / running sum)
 // softmax held in registers; quad reductions by warp shuffles.  Scores and probabilities never touch HBM.
-// Round-1 version uses mma.sync m16n8k16 bf16 (fp32 accumulate); the tcgen05 version is the planned upgrade
-// (attention is ~4 % of the step's FLOPs).
+// This is the mma.sync m16n8k16 (fp32 accumulate) variant.  The tcgen05 kernel in attention_tc.cu serves S <= 256;
+// this one remains for longer sequences (ViT-L/14, S = 257) and as an independent implementation for tests.
 #include "../../include/vlmclip.h"
 #include "common.cuh"
 
@@ -218,14 +218,12 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 }  // namespace
 }  // namespace vlmclip
 
-using namespace vlmclip;
+namespace vlmclip {
 
-extern "C" int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H,
-                                     int causal, float scale, void* stream) {
-  VLMCLIP_CHECK_ARG(qkv && out, "attention: null pointer");
-  VLMCLIP_CHECK_ARG(B > 0 && S > 0 && H > 0, "attention: bad dims B=%d S=%d H=%d", B, S, H);
-  VLMCLIP_CHECK_ARG(S <= 512, "attention: S=%d exceeds the shared-memory resident K/V limit (512)", S);
-  VLMCLIP_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0, "attention: pointers must be 16-byte aligned");
+// mma.sync fallback used for S > 256 (ViT-L/14, S = 257), where the single-pass tcgen05 kernel's N <= 256 limit
+// does not hold; same contract as vlmclip_attention_fwd.
+int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
+                           float scale, cudaStream_t stream) {
   const int nblocks = (S + 15) / 16;
   const int groups = (nblocks + 7) / 8;
   const int qw = (nblocks + groups - 1) / groups;
@@ -238,7 +236,9 @@ extern "C" int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* 
   }
   dim3 grid(B * H, groups);
   count_launch(1);
-  attention_fwd_kernel<<<grid, qw * 32, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, key_mask, S, H, causal, scale * 1.4426950408889634f, Spad);
+  attention_fwd_kernel<<<grid, qw * 32, smem, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, key_mask, S, H,
+                                                       causal, scale * 1.4426950408889634f, Spad);
   return report_cuda(cudaGetLastError(), "attention_fwd_kernel launch");
 }
+
+}  // namespace vlmclip
