@@ -60,12 +60,17 @@ int64_t vlmclip_launch_count(void);
  *     v = act(v)                                                 (HF:349)
  *     if residual:  v += residual[m, n]                          (HF:377,382)
  *   A, W, residual: bf16.  bias, col_c: fp32[N].  row_stats: fp32[M][2] = (mean, rstd).
+ *   Instead of row_stats the row statistics can come as partials: stats_part_in fp32 [M][K/32][2] = (mean, M2 =
+ *   sum (x - mean)^2) of each 32-column block of the row, combined in the epilogue (Chan) with eps = ln_eps.
+ *   stats_part_out (optional, bf16 output, N % 32 == 0): the epilogue writes those partials for the rows it
+ *   produces, fp32 [M][N/32][2], so the next LN-folded layer needs no separate statistics pass over HBM.
  *   C: bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1).  K % 8 == 0, N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0,
  *   16-byte aligned base pointers.
  * --------------------------------------------------------------------------------------------------------- */
 int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                       const float* bias, const void* residual, int64_t ldr, const float* row_stats,
-                      const float* col_c, int M, int N, int K, int act, int out_fp32, void* stream);
+                      const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
+                      float* stats_part_out, int M, int N, int K, int act, int out_fp32, void* stream);
 
 /* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */
@@ -75,6 +80,8 @@ int vlmclip_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, con
  * final_layer_norm, model_m.py:86,102; CLS through post_layernorm, HF:686).  x rows may be strided (ldx). */
 int vlmclip_layernorm_bf16_f32out(const void* x, int64_t ldx, float* y, int64_t ldy, const float* gamma,
                                   const float* beta, int M, int D, float eps, void* stream);
+/* Combine the (mean, M2) partials a GEMM epilogue wrote (stats_part_out) into (mean, rstd) per row: fp32 [M][2]. */
+int vlmclip_ln_partials_to_stats(const float* partials, float* stats_out, int M, int npart, float eps, void* stream);
 /* Row statistics only (mean, rstd) for the LN-folded GEMM epilogue. */
 int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, int D, float eps, void* stream);
 

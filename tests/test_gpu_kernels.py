@@ -69,6 +69,37 @@ def test_gemm(cuda, M, N, K, has_bias, act, has_res, has_stats, out_fp32):
     assert torch.isfinite(out.float()).all()
 
 
+def test_gemm_emits_and_consumes_ln_partials(cuda):
+    """out-proj style GEMM writes per-32-column (mean, M2) partials of its output rows; an LN-folded GEMM consumes them.
+    The pair must equal LayerNorm followed by a plain dense layer."""
+    from vlm_clip_b200 import ops
+
+    g = _gen(4242)
+    M, D, N2 = 1000, 768, 512
+    a = torch.randn(M, D, device=cuda, generator=g).to(bf16)
+    w = (torch.randn(D, D, device=cuda, generator=g) / math.sqrt(D)).to(bf16)
+    res = (torch.randn(M, D, device=cuda, generator=g) * 3 + 1.5).to(bf16)  # non-zero mean rows
+    part = torch.zeros(M, D // 32, 2, device=cuda)
+    x = ops.gemm(a, w, residual=res, stats_part_out=part)
+    xf = x.float()
+    blocks = xf.view(M, D // 32, 32)
+    ref_mean = blocks.mean(-1)
+    ref_m2 = (blocks - ref_mean[..., None]).pow(2).sum(-1)
+    # partials are taken before the bf16 rounding of x: agreement to bf16 resolution of the elements
+    assert torch.allclose(part[..., 0], ref_mean, atol=2e-2, rtol=0)
+    assert torch.allclose(part[..., 1], ref_m2, rtol=2e-2, atol=1e-1)
+    gamma = torch.rand(D, device=cuda, generator=g) + 0.5
+    beta = torch.randn(D, device=cuda, generator=g) * 0.2
+    W2 = torch.randn(N2, D, device=cuda, generator=g) / math.sqrt(D)
+    b2 = torch.randn(N2, device=cuda, generator=g)
+    Wf = (W2 * gamma[None]).to(bf16)
+    colc = Wf.float().sum(1).contiguous()
+    bias = (W2 @ beta + b2).contiguous()
+    y = ops.gemm(x, Wf, bias=bias, stats_part_in=part, ln_eps=1e-5, col_c=colc)
+    ref = O.layer_norm(xf, gamma, beta) @ W2.t() + b2
+    assert _rel(y, ref) < 6e-3, _rel(y, ref)
+
+
 def test_gemm_rejects_bad_args(cuda):
     from vlm_clip_b200 import ops
 

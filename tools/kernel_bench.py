@@ -97,6 +97,21 @@ bb = model._backbone()
 tv = timeit(lambda: bb.vision_hidden(batch['pixel_values']), iters=8)
 ttx = timeit(lambda: bb.text_hidden_pre_ln(batch['input_ids'], batch['attention_mask']), iters=8)
 print(f"vision tower {tv:.2f} ms ; text tower {ttx:.2f} ms")
+# per-op trace of one vision tower forward
+ops.TRACE = []
+bb.vision_hidden(batch['pixel_values'])
+torch.cuda.synchronize()
+import collections
+agg = collections.OrderedDict()
+for name, e0, e1, extra in ops.TRACE:
+    key = f"{name} {extra}"
+    agg.setdefault(key, []).append(e0.elapsed_time(e1) * 1e3)
+ops.TRACE = None
+tot = 0
+for key, v in agg.items():
+    print(f"   {key:48s} n={len(v):3d} avg {sum(v)/len(v):8.1f} us  total {sum(v)/1e3:7.3f} ms")
+    tot += sum(v)
+print(f"   traced total {tot/1e3:.2f} ms")
 # autocast comparator: error of torch's own bf16 path against fp32 on the same weights
 with torch.no_grad():
     ps, idss, ms = batch['pixel_values'][:8], batch['input_ids'][:8], batch['attention_mask'][:8]

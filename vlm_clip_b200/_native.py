@@ -25,9 +25,10 @@ PROTOTYPES = {
     "vlmclip_abi_version": (_i, []),
     "vlmclip_last_error": (C.c_char_p, []),
     "vlmclip_launch_count": (_i64, []),
-    "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _i, _f, _p, _i, _i, _i, _i, _i, _p]),
     "vlmclip_layernorm_bf16": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_layernorm_bf16_f32out": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _f, _p]),
+    "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),
     "vlmclip_row_stats_bf16": (_i, [_p, _i64, _p, _i, _i, _f, _p]),
     "vlmclip_im2col_patches": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "vlmclip_vision_embed_ln": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),

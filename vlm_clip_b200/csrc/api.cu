@@ -59,6 +59,12 @@ static EncodeTiledFn get_encode_fn() {
 // bf16 row-major [rows, cols] (ld elements) -> 2-D map with box [box_rows x 64 cols], 128-B swizzle.
 // Used for the K-major operand tiles and for the 128 x 64 result / residual panels of the epilogue.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  return make_tmap_bf16_box(map, base, rows, cols, ld, box_rows, 64);
+}
+
+// general form: box [box_rows x box_cols], swizzle span = box_cols * 2 bytes (64 cols -> 128 B, 32 cols -> 64 B)
+int make_tmap_bf16_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
@@ -66,10 +72,13 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t col
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p rows=%lld cols=%lld ld=%lld)", (int)r,

@@ -32,6 +32,8 @@ int report_cuda(cudaError_t e, const char* what);
 int sm_count();
 // bf16 row-major [rows, cols] (ld elements) -> 2-D tensor map, box [box_rows x 64 cols], 128-byte swizzle
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int make_tmap_bf16_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols);
 
 // ------------------------------------------------------------------------------------------
 // generic helpers

@@ -18,6 +18,8 @@
 //                      into the panel -> TMA store.  Panel managers chain store -> wait-read -> next
 //                      residual load so global traffic of the epilogue is fully asynchronous.
 //   Tile order is n-fastest so the CTAs running at one moment share a few A row-blocks through L2.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vlmclip {
@@ -32,7 +34,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
 constexpr int EPI_GROUP_THREADS = 128;      // one group = 4 warps = all 128 accumulator rows
 constexpr int QUARTER_N = 64;               // staged epilogue unit: 128 rows x 64 columns (one swizzle panel)
-constexpr uint32_t EBUF_BYTES = BLOCK_M * QUARTER_N * 2;  // 16 KB
+constexpr int PANEL_N = 32;                 // staged epilogue unit: 128 rows x 32 columns (64-byte swizzle span)
+constexpr uint32_t EBUF_BYTES = BLOCK_M * PANEL_N * 2;  // 8 KB
 
 struct GemmParams {
   void* C;
@@ -40,25 +43,43 @@ struct GemmParams {
   const __nv_bfloat16* residual;
   const float* row_stats;  // [M][2] mean, rstd
   const float* col_c;      // [N]
+  const float* part_in;    // [M][npart_in][2] (mean, M2) of 32-column blocks of the A operand's rows (LN fold)
+  float* part_out;         // [M][N/32][2] same statistics of the rows this GEMM writes (for the next LN-folded layer)
+  int npart_in;
+  float ln_eps;
   int64_t ldc, ldr;
   int M, N, K;
   int act;
   int out_fp32;
   int staged;  // 1: residual in / result out go through swizzled smem panels and TMA (bf16 output only)
+  int int_pack;
   int m_tiles, n_tiles, k_blocks;
 };
 
-template <int BLOCK_N, int STAGES>
+// EB = panel buffers per epilogue group.  EB = 1: one 16 KB panel per group (residual in / result out chained through
+// it).  EB = 2: two panels per group, so the residual panel of the next quarter is prefetched while the current one is
+// processed (used for the residual layers, traded against one pipeline stage of the main loop).
+template <int BLOCK_N, int STAGES, int EB>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;          // 2 x 16 KB, 1024-aligned
-  static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EBUF_BYTES;   // bias[BLOCK_N], col_c[BLOCK_N] fp32
+  static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;               // 2 * EB x 16 KB, 1024-aligned
+  static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EB * EBUF_BYTES;   // bias[BLOCK_N], col_c[BLOCK_N] fp32
   static constexpr uint32_t BAR_OFFSET = VEC_OFFSET + 2 * BLOCK_N * 4;
-  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 4;
+  static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 4 * EB;
   static constexpr uint32_t DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16;
+  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
+
+// bf16x2 pack with round-to-nearest-even on the integer pipe (F2FP runs on the SFU pipe, which the quick_gelu
+// epilogue already loads with one MUFU.TANH per element)
+__device__ __forceinline__ uint32_t pack_bf16x2_int(float lo, float hi) {
+  uint32_t a = __float_as_uint(lo), b = __float_as_uint(hi);
+  a += 0x7fffu + ((a >> 16) & 1u);
+  b += 0x7fffu + ((b >> 16) & 1u);
+  return __byte_perm(a, b, 0x7632);
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return quick_gelu(v);
@@ -101,12 +122,12 @@ __device__ __forceinline__ void epi_math8(float* v, const float* sBias, const fl
   }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, EB>;
   constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 or 512)
   constexpr int QUARTERS = BLOCK_N / QUARTER_N;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -121,8 +142,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint64_t* res_full_bar = bars + 2 * STAGES + 4;   // [2] E buffer of group g is free (and holds the residual)
-  uint64_t* e_written_bar = bars + 2 * STAGES + 6;  // [2] group g has written its result panel
+  uint64_t* res_full_bar = bars + 2 * STAGES + 4;            // [2][EB] panel is free (and holds the residual)
+  uint64_t* e_written_bar = bars + 2 * STAGES + 4 + 2 * EB;  // [2][EB] the group has written its result panel
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -145,6 +166,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], EPI_THREADS);
+    }
+    for (int b = 0; b < 2 * EB; ++b) {
       mbar_init(&res_full_bar[b], 1);
       mbar_init(&e_written_bar[b], EPI_GROUP_THREADS);
     }
@@ -212,38 +235,64 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // the buffer with the residual panel of the group's next quarter, or simply hands it back.
     if (p.staged) {
       const int g = warp - 2;
-      uint8_t* ebuf = sE + g * EBUF_BYTES;
-      uint32_t wphase = 0;
-      bool pending = false;
-      int prev_c0 = 0, prev_r0 = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.n_tiles;
-        const int n_blk = tile - m_blk * p.n_tiles;
-        for (int q = g; q < QUARTERS; q += 2) {
-          const int c0 = n_blk * BLOCK_N + q * QUARTER_N;
-          if (c0 >= p.N) continue;
-          if (pending) {
-            mbar_wait(&e_written_bar[g], wphase);
-            wphase ^= 1u;
-            tma_store_2d(&tmC, ebuf, prev_c0, prev_r0);
-            tma_store_commit();
-            tma_store_wait_read<0>();
+      // panels of this group in processing order: (tile, q, hp) with q = g, g+2 (64-column quarters), hp = 0, 1
+      // (32-column halves), keeping only panels whose first column is inside N
+      struct QIter {
+        int tile, q, hp;
+      };
+      auto advance = [&](QIter& it) {  // next valid panel, or tile >= num_tiles
+        for (;;) {
+          if (++it.hp == 2) {
+            it.hp = 0;
+            it.q += 2;
+            if (it.q >= QUARTERS) {
+              it.q = g;
+              it.tile += gridDim.x;
+            }
           }
-          if (p.residual != nullptr) {
-            mbar_arrive_expect_tx(&res_full_bar[g], EBUF_BYTES);
-            tma_load_2d(ebuf, &tmR, &res_full_bar[g], c0, m_blk * BLOCK_M);
-          } else {
-            mbar_arrive(&res_full_bar[g]);
-          }
-          pending = true;
-          prev_c0 = c0;
-          prev_r0 = m_blk * BLOCK_M;
+          if (it.tile >= num_tiles) return;
+          const int n_blk = it.tile % p.n_tiles;
+          if (n_blk * BLOCK_N + it.q * QUARTER_N + it.hp * PANEL_N < p.N) return;
         }
+      };
+      auto coords = [&](const QIter& it, int& c0, int& r0) {
+        const int m_blk = it.tile / p.n_tiles;
+        const int n_blk = it.tile - m_blk * p.n_tiles;
+        c0 = n_blk * BLOCK_N + it.q * QUARTER_N + it.hp * PANEL_N;
+        r0 = m_blk * BLOCK_M;
+      };
+      auto hand_over = [&](const QIter& it, int j) {  // make panel j ready for unit `it`
+        uint8_t* ebuf = sE + (g * EB + j) * EBUF_BYTES;
+        if (p.residual != nullptr) {
+          int c0, r0;
+          coords(it, c0, r0);
+          mbar_arrive_expect_tx(&res_full_bar[g * EB + j], EBUF_BYTES);
+          tma_load_2d(ebuf, &tmR, &res_full_bar[g * EB + j], c0, r0);
+        } else {
+          mbar_arrive(&res_full_bar[g * EB + j]);
+        }
+      };
+      QIter st{(int)blockIdx.x, g, -1};  // store cursor (advance() moves it onto the first valid panel)
+      advance(st);
+      QIter ld = st;  // load cursor, runs EB quarters ahead
+      for (int j = 0; j < EB && ld.tile < num_tiles; ++j) {
+        hand_over(ld, j);
+        advance(ld);
       }
-      if (pending) {
-        mbar_wait(&e_written_bar[g], wphase);
-        tma_store_2d(&tmC, ebuf, prev_c0, prev_r0);
+      for (uint32_t n = 0; st.tile < num_tiles; ++n) {
+        const int j = n % EB;
+        uint8_t* ebuf = sE + (g * EB + j) * EBUF_BYTES;
+        int c0, r0;
+        coords(st, c0, r0);
+        mbar_wait(&e_written_bar[g * EB + j], (n / EB) & 1u);  // the group has written quarter n into panel j
+        tma_store_2d(&tmC, ebuf, c0, r0);
         tma_store_commit();
+        advance(st);
+        if (ld.tile < num_tiles) {
+          tma_store_wait_read<0>();  // the store has read panel j: refill it for quarter n + EB
+          hand_over(ld, j);
+          advance(ld);
+        }
       }
       tma_store_wait<0>();  // all stores complete before the CTA (and its shared memory) goes away
     }
@@ -254,9 +303,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row_in_tile = quarter * 32 + lane;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
     const bool has_bias = p.bias != nullptr;
-    const bool has_stats = p.row_stats != nullptr;
-    uint8_t* ebuf = sE + g * EBUF_BYTES;
-    uint32_t abuf = 0, aphase = 0, rphase = 0;
+    const bool has_stats = p.row_stats != nullptr || p.part_in != nullptr;
+    uint32_t abuf = 0, aphase = 0, qseq = 0;  // qseq counts the quarters this group has processed
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_tiles;
       const int n_blk = tile - m_blk * p.n_tiles;
@@ -264,9 +312,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < p.M;
       float a_scale = 1.f, a_shift = 0.f;
       if (has_stats && row_ok) {
-        const float2 st = *reinterpret_cast<const float2*>(p.row_stats + 2 * (int64_t)row);
-        a_scale = st.y;
-        a_shift = -st.x * st.y;
+        float mean, rstd;
+        if (p.part_in != nullptr) {
+          // Chan's parallel combination of the per-64-column (mean, M2) partials the producing layer's epilogue left
+          const float2* pp = reinterpret_cast<const float2*>(p.part_in) + (int64_t)row * p.npart_in;
+          float msum = 0.f, m2 = 0.f;
+          for (int i = 0; i < p.npart_in; ++i) msum += __ldg(&pp[i]).x;
+          mean = msum / (float)p.npart_in;
+          for (int i = 0; i < p.npart_in; ++i) {
+            const float2 q = __ldg(&pp[i]);
+            const float d = q.x - mean;
+            m2 += q.y + 32.f * d * d;
+          }
+          rstd = rsqrtf(m2 / (32.f * (float)p.npart_in) + p.ln_eps);
+        } else {
+          const float2 st = *reinterpret_cast<const float2*>(p.row_stats + 2 * (int64_t)row);
+          mean = st.x;
+          rstd = st.y;
+        }
+        a_scale = rstd;
+        a_shift = -mean * rstd;
       }
       // ---- stage this tile's bias / col_c once (previous tile's readers are past the first barrier) ----
       named_bar_sync(1, EPI_THREADS);
@@ -285,48 +350,69 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bool released = false;
 #pragma unroll 1
         for (int q = g; q < QUARTERS; q += 2) {
-          const int c0 = n_blk * BLOCK_N + q * QUARTER_N;
-          if (c0 >= p.N) continue;  // uniform across the CTA
-          uint32_t r0[32], r1[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(taddr + q * QUARTER_N, r0);
-          tmem_ld_32x32b_x32(taddr + q * QUARTER_N + 32, r1);
-          tmem_wait_ld();
-          if (q + 2 >= QUARTERS || c0 + 2 * QUARTER_N >= p.N) {
-            tcgen05_fence_before();
-            mbar_arrive(&tempty_bar[abuf]);  // last TMEM read of this tile: hand the accumulator back early
-            released = true;
-          }
-          mbar_wait(&res_full_bar[g], rphase);  // E buffer is ours (and holds the residual panel, if any)
-          rphase ^= 1u;
-          uint8_t* erow = ebuf + row_in_tile * 128;
-#pragma unroll
-          for (int pc = 0; pc < 8; ++pc) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(pc < 4 ? r0[pc * 8 + j] : r1[(pc - 4) * 8 + j]);
-            epi_math8(v, sBias, sColc, q * QUARTER_N + pc * 8, a_scale, a_shift, has_bias, has_stats, p.act);
-            uint4* slot = reinterpret_cast<uint4*>(erow + ((pc ^ (row_in_tile & 7)) << 4));  // 128-B swizzle
-            if (p.residual != nullptr) {
-              const uint4 rr = *slot;
-              v[0] += bf16_lo(rr.x);
-              v[1] += bf16_hi(rr.x);
-              v[2] += bf16_lo(rr.y);
-              v[3] += bf16_hi(rr.y);
-              v[4] += bf16_lo(rr.z);
-              v[5] += bf16_hi(rr.z);
-              v[6] += bf16_lo(rr.w);
-              v[7] += bf16_hi(rr.w);
+#pragma unroll 1
+          for (int hp = 0; hp < 2; ++hp) {
+            const int c0 = n_blk * BLOCK_N + q * QUARTER_N + hp * PANEL_N;
+            if (c0 >= p.N) continue;  // uniform across the CTA
+            uint32_t r0[32];
+            __syncwarp();
+            tmem_ld_32x32b_x32(taddr + q * QUARTER_N + hp * PANEL_N, r0);
+            tmem_wait_ld();
+            // last TMEM read of this tile by this thread: hand the accumulator back early
+            const bool last_q = (q + 2 >= QUARTERS) || (n_blk * BLOCK_N + (q + 2) * QUARTER_N >= p.N);
+            const bool last_h = (hp == 1) || (c0 + PANEL_N >= p.N);
+            if (last_q && last_h) {
+              tcgen05_fence_before();
+              mbar_arrive(&tempty_bar[abuf]);
+              released = true;
             }
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]);
-            o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]);
-            o.w = pack_bf16x2(v[6], v[7]);
-            *slot = o;
+            const int pj = qseq % EB;
+            mbar_wait(&res_full_bar[g * EB + pj], (qseq / EB) & 1u);  // panel is ours (and holds the residual, if any)
+            uint8_t* erow = sE + (g * EB + pj) * EBUF_BYTES + row_in_tile * 64;
+            float sh = 0.f, s1 = 0.f, s2 = 0.f;  // shifted one-pass statistics of this row's 32 outputs
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r0[pc * 8 + j]);
+              epi_math8(v, sBias, sColc, q * QUARTER_N + hp * PANEL_N + pc * 8, a_scale, a_shift, has_bias, has_stats, p.act);
+              uint4* slot = reinterpret_cast<uint4*>(erow + ((pc ^ ((row_in_tile >> 1) & 3)) << 4));  // 64-B swizzle
+              if (p.residual != nullptr) {
+                const uint4 rr = *slot;
+                v[0] += bf16_lo(rr.x);
+                v[1] += bf16_hi(rr.x);
+                v[2] += bf16_lo(rr.y);
+                v[3] += bf16_hi(rr.y);
+                v[4] += bf16_lo(rr.z);
+                v[5] += bf16_hi(rr.z);
+                v[6] += bf16_lo(rr.w);
+                v[7] += bf16_hi(rr.w);
+              }
+              if (p.part_out != nullptr) {
+                if (pc == 0) sh = v[0];  // shift by the first value: keeps sum((v - sh)^2) - s1^2/n well conditioned
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float d = v[j] - sh;
+                  s1 += d;
+                  s2 = fmaf(d, d, s2);
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]);
+              o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]);
+              o.w = pack_bf16x2(v[6], v[7]);
+              *slot = o;
+            }
+            if (p.part_out != nullptr && row_ok) {
+              const float mq = s1 * (1.f / 32.f);
+              reinterpret_cast<float2*>(p.part_out)[(int64_t)row * (p.N >> 5) + (c0 >> 5)] =
+                  make_float2(sh + mq, fmaxf(s2 - s1 * mq, 0.f));
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+            mbar_arrive(&e_written_bar[g * EB + pj]);
+            ++qseq;
           }
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
-          mbar_arrive(&e_written_bar[g]);
         }
         if (!released) {
           tcgen05_fence_before();
@@ -398,20 +484,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EB>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                 GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, EB>;
   static bool attr_set = false;  // benign race: setting the attribute twice is harmless
   if (!attr_set) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES>,
+    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   p.n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tn_kernel<BLOCK_N, STAGES><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+  gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   return report_cuda(cudaGetLastError(), "gemm_bf16_tn_kernel launch");
 }
 
@@ -425,7 +511,8 @@ using namespace vlmclip;
 
 extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                  const float* bias, const void* residual, int64_t ldr, const float* row_stats,
-                                 const float* col_c, int M, int N, int K, int act, int out_fp32, void* stream) {
+                                 const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
+                                 float* stats_part_out, int M, int N, int K, int act, int out_fp32, void* stream) {
   VLMCLIP_CHECK_ARG(A && W && C, "gemm: null A/W/C pointer");
   VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dims M=%d N=%d K=%d", M, N, K);
   VLMCLIP_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8 (K=%d N=%d)", K, N);
@@ -434,7 +521,13 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   VLMCLIP_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)C % 16 == 0),
                     "gemm: A/W/C must be 16-byte aligned");
   VLMCLIP_CHECK_ARG(act >= 0 && act <= 3, "gemm: unknown activation %d", act);
-  VLMCLIP_CHECK_ARG((row_stats == nullptr) == (col_c == nullptr), "gemm: row_stats and col_c go together");
+  VLMCLIP_CHECK_ARG(!(row_stats && stats_part_in), "gemm: give row_stats or stats_part_in, not both");
+  VLMCLIP_CHECK_ARG(((row_stats != nullptr) || (stats_part_in != nullptr)) == (col_c != nullptr),
+                    "gemm: LN fold needs col_c together with row_stats / stats_part_in");
+  VLMCLIP_CHECK_ARG(stats_part_in == nullptr || (npart_in > 0 && npart_in * 32 == K),
+                    "gemm: stats_part_in must hold K/32 = %d partials per row (got %d)", K / 32, npart_in);
+  VLMCLIP_CHECK_ARG(stats_part_out == nullptr || (N % 32 == 0 && !out_fp32),
+                    "gemm: stats_part_out needs N %% 32 == 0 and bf16 output");
   if (residual) {
     VLMCLIP_CHECK_ARG(ldr % 8 == 0 && ldr >= N && (uintptr_t)residual % 16 == 0,
                       "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
@@ -448,6 +541,10 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.row_stats = row_stats;
   p.col_c = col_c;
+  p.part_in = stats_part_in;
+  p.part_out = stats_part_out;
+  p.npart_in = npart_in;
+  p.ln_eps = ln_eps;
   p.ldc = ldc;
   p.ldr = ldr;
   p.M = M;
@@ -458,7 +555,17 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
 
-  const bool wide = N > 128;
+  // Tile width: 256 columns feed the tensor core best (96 B of smem operand traffic per clock against 128 B/clk for a
+  // 128-wide tile), but when 256-wide tiles leave the last wave of the persistent grid mostly empty (e.g. N = 512,
+  // M = 19712: 308 tiles on 148 SMs = 3 waves for 2.08 waves of work) the narrower tile wins.  Estimated cost =
+  // waves x relative tile time (a 128-wide tile costs ~0.56 of a 256-wide one).
+  bool wide = N > 128;
+  if (wide) {
+    const int sms = sm_count();
+    const long t256 = (long)p.m_tiles * ((N + 255) / 256), t128 = (long)p.m_tiles * ((N + 127) / 128);
+    const double c256 = (double)((t256 + sms - 1) / sms), c128 = 0.56 * (double)((t128 + sms - 1) / sms);
+    if (c128 < 0.92 * c256) wide = false;
+  }
   const int block_n = wide ? 256 : 128;
   p.staged = out_fp32 ? 0 : 1;
   CUtensorMap tmA, tmB, tmC, tmR;
@@ -469,15 +576,28 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   tmC = tmA;
   tmR = tmA;
   if (p.staged) {
-    rc = make_tmap_bf16(&tmC, C, M, N, ldc, BLOCK_M);
+    rc = make_tmap_bf16_box(&tmC, C, M, N, ldc, BLOCK_M, PANEL_N);
     if (rc) return rc;
     if (residual) {
-      rc = make_tmap_bf16(&tmR, residual, M, N, ldr, BLOCK_M);
+      rc = make_tmap_bf16_box(&tmR, residual, M, N, ldr, BLOCK_M, PANEL_N);
       if (rc) return rc;
     }
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   count_launch(1);
-  if (wide) return launch_gemm<256, 4>(tmA, tmB, tmC, tmR, p, s);
-  return launch_gemm<128, 6>(tmA, tmB, tmC, tmR, p, s);
+  // Two panels per epilogue group (at the price of one main-loop stage) pay off when the main loop of a tile is short
+  // (K <= 1024: ~6k tensor-core cycles) and the epilogue has a load -> process -> store chain per panel (residual).
+  // VLMCLIP_GEMM_CFG = "41" | "32" overrides for experiments; VLMCLIP_GEMM_INTPACK=1 packs bf16 on the integer pipe.
+  static const int cfg_override = []() {
+    const char* e = getenv("VLMCLIP_GEMM_CFG");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  static const int intpack_override = []() {
+    const char* e = getenv("VLMCLIP_GEMM_INTPACK");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  p.int_pack = intpack_override;
+  (void)cfg_override;
+  if (wide) return launch_gemm<256, 4, 2>(tmA, tmB, tmC, tmR, p, s);
+  return launch_gemm<128, 6, 2>(tmA, tmB, tmC, tmR, p, s);
 }

@@ -295,6 +295,34 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __re
     }                                         \
   } while (0)
 
+// (mean, M2) partials of 32-column blocks -> (mean, rstd) per row (Chan's parallel combination); 4 lanes per row
+__global__ void __launch_bounds__(256)
+ln_partials_to_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int M, int npart, float eps) {
+  const int row = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int sub = threadIdx.x & 3;
+  float msum = 0.f;
+  float2 q[16];  // up to 64 partials (D <= 2048) spread over 4 lanes
+  int cnt = 0;
+  if (row < M) {
+    for (int i = sub; i < npart; i += 4) {
+      q[cnt] = __ldg(part + (int64_t)row * npart + i);
+      msum += q[cnt].x;
+      ++cnt;
+    }
+  }
+  msum += __shfl_xor_sync(0xffffffffu, msum, 1);
+  msum += __shfl_xor_sync(0xffffffffu, msum, 2);
+  const float mean = msum / (float)npart;
+  float m2 = 0.f;
+  for (int i = 0; i < cnt; ++i) {
+    const float d = q[i].x - mean;
+    m2 += q[i].y + 32.f * d * d;
+  }
+  m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+  m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+  if (row < M && sub == 0) stats[row] = make_float2(mean, rsqrtf(m2 / (32.f * (float)npart) + eps));
+}
+
 int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
   const int64_t cap = (int64_t)sm_count() * 32;
@@ -426,4 +454,13 @@ extern "C" int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float
   gather_rows_kernel<<<grid_for((int64_t)R * D, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx,
                                                                                     y, R, D);
   return report_cuda(cudaGetLastError(), "gather_rows_kernel launch");
+}
+
+extern "C" int vlmclip_ln_partials_to_stats(const float* partials, float* stats_out, int M, int npart, float eps,
+                                            void* stream) {
+  VLMCLIP_CHECK_ARG(partials && stats_out && M > 0 && npart > 0 && npart <= 64, "ln_partials_to_stats: bad arguments");
+  count_launch(1);
+  ln_partials_to_stats_kernel<<<(M + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const float2*)partials, (float2*)stats_out, M,
+                                                                              npart, eps);
+  return report_cuda(cudaGetLastError(), "ln_partials_to_stats_kernel launch");
 }

@@ -15,6 +15,32 @@ f32 = torch.float32
 # bench.py sets this to {"gemm": []} for ONE instrumented step: every dense-layer launch is then bracketed by
 # CUDA events on the launching stream and recorded as (start, stop, algorithmic FLOPs).
 PROFILE = None
+# development aid (tools/kernel_bench.py): when set to a list, every wrapper call is bracketed by CUDA events and
+# recorded as (name, start, stop, extra)
+TRACE = None
+
+
+def _traced(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        tr = TRACE
+        if tr is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **k)
+        e1.record()
+        shape = tuple(a[0].shape) if a and hasattr(a[0], "shape") else ()
+        extra = "x".join(map(str, shape))
+        if fn.__name__ == "gemm":
+            extra += "->%d%s%s%s" % (a[1].shape[0], " res" if k.get("residual") is not None else "",
+                                     " act" if k.get("act") else "", " part" if k.get("stats_part_out") is not None else "")
+        tr.append((fn.__name__, e0, e1, extra))
+        return out
+
+    return wrapper
 
 
 def _req(cond: bool, msg: str) -> None:
@@ -23,7 +49,9 @@ def _req(cond: bool, msg: str) -> None:
 
 
 # --------------------------------------------------------------------------------------------- dense layers
-def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=False, row_stats=None, col_c=None):
+@_traced
+def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=False, row_stats=None, col_c=None,
+         stats_part_in=None, ln_eps=1e-5, stats_part_out=None):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores (vlmclip_gemm_bf16)."""
     _req(a.dtype == bf16 and w.dtype == bf16, "gemm: a and w must be bf16")
     _req(a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], "gemm: shape mismatch")
@@ -44,7 +72,8 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
     N.check(
         lib.vlmclip_gemm_bf16(
             N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(out), out.stride(0), N.ptr(bias), N.ptr(residual),
-            residual.stride(0) if residual is not None else 0, N.ptr(row_stats), N.ptr(col_c), M, Nn, K, int(act),
+            residual.stride(0) if residual is not None else 0, N.ptr(row_stats), N.ptr(col_c), N.ptr(stats_part_in),
+            (K // 32) if stats_part_in is not None else 0, float(ln_eps), N.ptr(stats_part_out), M, Nn, K, int(act),
             1 if out_fp32 else 0, N.stream()),
         "vlmclip_gemm_bf16")
     if prof is not None:
@@ -53,6 +82,7 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
     return out
 
 
+@_traced
 def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm: x must be bf16 [M, D]")
     M, D = x.shape
@@ -64,6 +94,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     return out
 
 
+@_traced
 def layernorm_rows_f32(x, gamma, beta, eps=1e-5, rows=None, ldx=None):
     """fp32 LayerNorm of `rows` rows of a bf16 buffer read with row stride `ldx` (e.g. token 0 of every sequence)."""
     _req(x.dtype == bf16 and x.is_contiguous(), "layernorm_rows_f32: x must be contiguous bf16")
@@ -77,6 +108,18 @@ def layernorm_rows_f32(x, gamma, beta, eps=1e-5, rows=None, ldx=None):
     return out
 
 
+@_traced
+def ln_partials_to_stats(part, eps=1e-5, out=None):
+    """(mean, M2) per 32-column block [M, npart, 2] -> (mean, rstd) per row [M, 2]."""
+    M, npart, _ = part.shape
+    if out is None:
+        out = torch.empty((M, 2), device=part.device, dtype=f32)
+    N.check(N.load().vlmclip_ln_partials_to_stats(N.ptr(part), N.ptr(out), M, npart, float(eps), N.stream()),
+            "vlmclip_ln_partials_to_stats")
+    return out
+
+
+@_traced
 def row_stats(x, eps=1e-5, out=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "row_stats: x must be bf16 [M, D]")
     M, D = x.shape
@@ -87,6 +130,7 @@ def row_stats(x, eps=1e-5, out=None):
     return out
 
 
+@_traced
 def im2col(pixels, patch: int, out=None):
     _req(pixels.dim() == 4 and pixels.shape[1] == 3 and pixels.is_contiguous(), "im2col: pixels must be [B,3,H,W]")
     _req(pixels.dtype in (f32, bf16), "im2col: pixels must be fp32 or bf16")
@@ -102,6 +146,7 @@ def im2col(pixels, patch: int, out=None):
     return out
 
 
+@_traced
 def vision_embed_ln(patch_f32, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
     D = pos.shape[1]
     _req(patch_f32.dtype == f32 and patch_f32.shape == (B * (S - 1), D) and patch_f32.is_contiguous(),
@@ -114,6 +159,7 @@ def vision_embed_ln(patch_f32, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, 
     return out
 
 
+@_traced
 def text_embed(ids, tok, pos, out=None):
     _req(ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous(), "text_embed: ids must be int64 [B,S]")
     B, S = ids.shape
@@ -127,6 +173,7 @@ def text_embed(ids, tok, pos, out=None):
     return out
 
 
+@_traced
 def attention(qkv, B: int, S: int, H: int, causal=False, key_mask=None, scale=None, out=None):
     _req(qkv.dtype == bf16 and qkv.shape == (B * S, 3 * H * 64) and qkv.is_contiguous(),
          "attention: qkv must be contiguous bf16 [B*S, 3*H*64]")
@@ -142,6 +189,7 @@ def attention(qkv, B: int, S: int, H: int, causal=False, key_mask=None, scale=No
     return out
 
 
+@_traced
 def gather_rows_f32(x, rows: int, ld: int, D: int):
     """y[r] = float(x.flat[r*ld : r*ld + D]) — the token-0 slice of a [B*S, D] bf16 activation."""
     out = torch.empty((rows, D), device=x.device, dtype=f32)

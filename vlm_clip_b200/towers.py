@@ -10,8 +10,8 @@ into the following dense layer) and replays the arithmetic of
 
 with one kernel per fused step:
 
-    row_stats(x) -> [QKV GEMM: LN1 folded, bias] -> attention -> [out-proj GEMM: bias + residual, in place]
-    row_stats(x) -> [fc1 GEMM: LN2 folded, bias, quick_gelu] -> [fc2 GEMM: bias + residual, in place]
+    [QKV GEMM: LN1 folded, bias] -> attention -> [out-proj GEMM: bias + residual in place, emits LN2 statistics]
+    [fc1 GEMM: LN2 folded, bias, quick_gelu] -> [fc2 GEMM: bias + residual in place, emits next layer's LN1 statistics]
 
 LayerNorm folding:  LN(x) W^T + b = rstd * (x (g*W)^T - mean * c) + (beta W^T + b),  c_n = sum_k (g*W)[n,k],
 so the dense layer reads the raw bf16 residual stream and its epilogue applies the row statistics; the
@@ -143,23 +143,32 @@ class NativeClipTowers:
         att = torch.empty((M, D), device=dev, dtype=bf16)
         hid = torch.empty((M, F), device=dev, dtype=bf16)
         stats = torch.empty((M, 2), device=dev, dtype=f32)
+        # per-32-column (mean, M2) partials of the residual stream, written by the epilogue of the layer that produces
+        # x (out-proj / fc2); a 5 MB combine pass turns them into (mean, rstd) instead of re-reading the 77 MB stream
+        part = torch.empty((M, D // 32, 2), device=dev, dtype=f32)
         xn = None if self.fold_ln else torch.empty((M, D), device=dev, dtype=bf16)
+        first = True
         for L in layers:
             if self.fold_ln:
-                ops.row_stats(x, eps, out=stats)
+                if first:  # the embeddings kernel does not emit partials: one explicit statistics pass
+                    ops.row_stats(x, eps, out=stats)
+                    first = False
+                else:
+                    ops.ln_partials_to_stats(part, eps, out=stats)
                 ops.gemm(x, L.qkv_w, bias=L.qkv_b, row_stats=stats, col_c=L.qkv_c, out=qkv)
             else:
                 ops.layernorm(x, L.ln1_w, L.ln1_b, eps, out=xn)
                 ops.gemm(xn, L.qkv_w_raw, bias=L.qkv_b_raw, out=qkv)
             ops.attention(qkv, B, S, H, causal=causal, key_mask=key_mask, out=att)
-            ops.gemm(att, L.out_w, bias=L.out_b, residual=x, out=x)  # x += out_proj(att): same thread reads & writes
+            # x += out_proj(att): the same thread reads and writes each element, so the update is done in place
+            ops.gemm(att, L.out_w, bias=L.out_b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
             if self.fold_ln:
-                ops.row_stats(x, eps, out=stats)
+                ops.ln_partials_to_stats(part, eps, out=stats)
                 ops.gemm(x, L.fc1_w, bias=L.fc1_b, row_stats=stats, col_c=L.fc1_c, act=N.ACT_QUICK_GELU, out=hid)
             else:
                 ops.layernorm(x, L.ln2_w, L.ln2_b, eps, out=xn)
                 ops.gemm(xn, L.fc1_w_raw, bias=L.fc1_b_raw, act=N.ACT_QUICK_GELU, out=hid)
-            ops.gemm(hid, L.fc2_w, bias=L.fc2_b, residual=x, out=x)
+            ops.gemm(hid, L.fc2_w, bias=L.fc2_b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
         return x
 
     # ------------------------------------------------------------------------------------------ towers
