@@ -18,6 +18,7 @@
 //                      into the panel -> TMA store.  Panel managers chain store -> wait-read -> next
 //                      residual load so global traffic of the epilogue is fully asynchronous.
 //   Tile order is n-fastest so the CTAs running at one moment share a few A row-blocks through L2.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -51,6 +52,7 @@ struct GemmParams {
   int M, N, K;
   int act;
   int out_fp32;
+  int debug;   // VLMCLIP_GEMM_DEBUG=1: one epilogue warp prints per-phase cycle totals (development aid)
   int staged;  // 1: residual in / result out go through swizzled smem panels and TMA (bf16 output only)
   int int_pack;
   int m_tiles, n_tiles, k_blocks;
@@ -59,10 +61,10 @@ struct GemmParams {
 // EB = panel buffers per epilogue group.  EB = 1: one 16 KB panel per group (residual in / result out chained through
 // it).  EB = 2: two panels per group, so the residual panel of the next quarter is prefetched while the current one is
 // processed (used for the residual layers, traded against one pipeline stage of the main loop).
-template <int BLOCK_N, int STAGES, int EB>
+template <int BLOCK_N, int STAGES, int EB, bool PAIR = false>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // a CTA pair splits W along N
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;               // 2 * EB x 16 KB, 1024-aligned
   static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EB * EBUF_BYTES;   // bias[BLOCK_N], col_c[BLOCK_N] fp32
@@ -122,12 +124,24 @@ __device__ __forceinline__ void epi_math8(float* v, const float* sBias, const fl
   }
 }
 
-template <int BLOCK_N, int STAGES, int EB>
+// PAIR = true: the kernel is launched in clusters of two CTAs (cta_group::2).  Each CTA owns 128 rows of a 256-row
+// tile (its own A tile, accumulator, epilogue) and loads HALF of the W tile; the leader CTA's MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both halves.  W bytes per SM and the smem operand traffic halve,
+// which also frees shared memory for more pipeline stages.
+// EPI selects a compile-time epilogue so each instantiation carries only the code it executes (the fully unrolled
+// generic epilogue is ~90 KB of SASS and thrashes the instruction cache: stall_no_inst was a top stall reason):
+//   EPI_GENERIC   everything decided at run time (tests, odd combinations, fp32 / direct output)
+//   EPI_FOLD      LN fold + bias                     (QKV)
+//   EPI_FOLD_ACT  LN fold + bias + quick_gelu        (fc1)
+//   EPI_RES       bias + residual + LN partials out  (out-proj, fc2)
+enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3 };
+
+template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES, EB>;
+  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR>;
   constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 or 512)
   constexpr int QUARTERS = BLOCK_N / QUARTER_N;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,24 +162,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader
+  // epilogue switches: compile-time constants for the specialised instantiations
+  const bool k_staged = EPI == EPI_GENERIC ? p.staged != 0 : true;
+  const bool k_has_res = EPI == EPI_GENERIC ? p.residual != nullptr : EPI == EPI_RES;
+  const bool k_has_bias = EPI == EPI_GENERIC ? p.bias != nullptr : true;
+  const bool k_has_stats = EPI == EPI_GENERIC ? (p.row_stats != nullptr || p.part_in != nullptr)
+                                              : (EPI == EPI_FOLD || EPI == EPI_FOLD_ACT);
+  const bool k_part_out = EPI == EPI_GENERIC ? p.part_out != nullptr : (EPI == EPI_RES && p.part_out != nullptr);
+  const int k_act = EPI == EPI_GENERIC ? p.act : (EPI == EPI_FOLD_ACT ? 1 : 0);
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker index (CTA or CTA pair)
+  const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzled tiles need a 1024-B aligned base
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.staged) {
+    if (k_staged) {
       tma_prefetch_desc(&tmC);
-      if (p.residual != nullptr) tma_prefetch_desc(&tmR);
+      if (k_has_res) tma_prefetch_desc(&tmR);
     }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);  // pair: only the leader arrives (expecting both CTAs' bytes); see the producer
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], EPI_THREADS);
+      mbar_init(&tempty_bar[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS);  // pair: both CTAs' epilogues release the leader
     }
     for (int b = 0; b < 2 * EB; ++b) {
       mbar_init(&res_full_bar[b], 1);
@@ -174,26 +199,45 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (PAIR)
+      tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else
+      tmem_alloc<TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  else
+    __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // pair: tiles are 256 rows tall (m index counts pair tiles); this CTA's 128-row block is 2*m + rank
+  const int num_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles;
-      const int n_blk = tile - m_blk * p.n_tiles;
+    for (int tile = unit; tile < num_tiles; tile += n_units) {
+      const int m_t = tile / p.n_tiles;
+      const int n_blk = tile - m_t * p.n_tiles;
+      const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-        tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+        if (PAIR) {
+          // Both CTAs' loads complete on the LEADER's full barrier; the leader alone arrives, expecting the bytes of both
+          // CTAs.  The peer needs no arrival of its own: its loads for the next round of this stage are issued only
+          // after its empty barrier fired, i.e. after the leader's MMAs consumed (hence completed) the current phase,
+          // and bytes landing before the leader's expect_tx merely drive the tx-count negative for a moment.
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          tma_load_2d_pair(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d_pair(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K,
+                           n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -201,39 +245,52 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
-    uint32_t stage = 0, phase = 0;
-    uint32_t abuf = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty_bar[abuf], aphase ^ 1u);
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + abuf * BLOCK_N;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== MMA issuer (pair: leader CTA only) =====================
+    if (!PAIR || cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      uint32_t stage = 0, phase = 0;
+      uint32_t abuf = 0, aphase = 0;
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
+        mbar_wait(&tempty_bar[abuf], aphase ^ 1u);
         tcgen05_fence_after();
-        const uint64_t a_desc = make_umma_desc_sw128(smem_u32(sA + stage * L::A_BYTES));
-        const uint64_t b_desc = make_umma_desc_sw128(smem_u32(sB + stage * L::B_BYTES));
+        const uint32_t d_tmem = tmem_base + abuf * BLOCK_N;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t a_desc = make_umma_desc_sw128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t b_desc = make_umma_desc_sw128(smem_u32(sB + stage * L::B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
-          umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
+            if (PAIR)
+              umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR)
+            umma_commit_pair(&empty_bar[stage]);
+          else
+            umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        // accumulator complete -> epilogue(s)
+        if (PAIR)
+          umma_commit_pair(&tfull_bar[abuf]);
+        else
+          umma_commit(&tfull_bar[abuf]);
+        abuf ^= 1u;
+        if (abuf == 0) aphase ^= 1u;
       }
-      umma_commit(&tfull_bar[abuf]);  // accumulator complete -> epilogue
-      abuf ^= 1u;
-      if (abuf == 0) aphase ^= 1u;
     }
   } else if ((warp == 2 || warp == 3) && lane == 0) {
     // ===================== epilogue panel manager of group g =====================
     // Owns E buffer g: TMA-stores the panel the group has written, then (once the store has read it) refills
     // the buffer with the residual panel of the group's next quarter, or simply hands it back.
-    if (p.staged) {
+    if (k_staged) {
       const int g = warp - 2;
       // panels of this group in processing order: (tile, q, hp) with q = g, g+2 (64-column quarters), hp = 0, 1
       // (32-column halves), keeping only panels whose first column is inside N
@@ -247,7 +304,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             it.q += 2;
             if (it.q >= QUARTERS) {
               it.q = g;
-              it.tile += gridDim.x;
+              it.tile += n_units;
             }
           }
           if (it.tile >= num_tiles) return;
@@ -256,14 +313,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       };
       auto coords = [&](const QIter& it, int& c0, int& r0) {
-        const int m_blk = it.tile / p.n_tiles;
-        const int n_blk = it.tile - m_blk * p.n_tiles;
+        const int m_t = it.tile / p.n_tiles;
+        const int n_blk = it.tile - m_t * p.n_tiles;
         c0 = n_blk * BLOCK_N + it.q * QUARTER_N + it.hp * PANEL_N;
-        r0 = m_blk * BLOCK_M;
+        r0 = (PAIR ? 2 * m_t + (int)cta_rank : m_t) * BLOCK_M;
       };
       auto hand_over = [&](const QIter& it, int j) {  // make panel j ready for unit `it`
         uint8_t* ebuf = sE + (g * EB + j) * EBUF_BYTES;
-        if (p.residual != nullptr) {
+        if (k_has_res) {
           int c0, r0;
           coords(it, c0, r0);
           mbar_arrive_expect_tx(&res_full_bar[g * EB + j], EBUF_BYTES);
@@ -272,7 +329,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_arrive(&res_full_bar[g * EB + j]);
         }
       };
-      QIter st{(int)blockIdx.x, g, -1};  // store cursor (advance() moves it onto the first valid panel)
+      QIter st{unit, g, -1};  // store cursor (advance() moves it onto the first valid panel)
       advance(st);
       QIter ld = st;  // load cursor, runs EB quarters ahead
       for (int j = 0; j < EB && ld.tile < num_tiles; ++j) {
@@ -302,51 +359,72 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
-    const bool has_bias = p.bias != nullptr;
-    const bool has_stats = p.row_stats != nullptr || p.part_in != nullptr;
+    const bool has_bias = k_has_bias;
+    const bool has_stats = k_has_stats;
     uint32_t abuf = 0, aphase = 0, qseq = 0;  // qseq counts the quarters this group has processed
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles;
-      const int n_blk = tile - m_blk * p.n_tiles;
+    long long tk[6] = {0, 0, 0, 0, 0, 0};
+    int ntl = 0;
+    const bool dbg = p.debug != 0 && blockIdx.x == 0 && (warp == EPI_WARP0 || warp == EPI_WARP0 + 4) && lane == 0;
+    // Per-tile scalars (this thread's bias / col_c element for the smem staging, its row's mean / rstd) are fetched one
+    // tile ahead, so their global-load latency never sits on the epilogue's critical path.
+    float pf_bias = 0.f, pf_colc = 0.f, pf_mean = 0.f, pf_rstd = 1.f;
+    auto prefetch_tile = [&](int tile) {
+      if (tile >= num_tiles) return;
+      const int m_t = tile / p.n_tiles;
+      const int n_blk = tile - m_t * p.n_tiles;
+      const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
       const int row = m_blk * BLOCK_M + row_in_tile;
-      const bool row_ok = row < p.M;
-      float a_scale = 1.f, a_shift = 0.f;
-      if (has_stats && row_ok) {
-        float mean, rstd;
+      const int col = n_blk * BLOCK_N + et;
+      pf_bias = (has_bias && et < BLOCK_N && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      pf_colc = (has_stats && et < BLOCK_N && col < p.N) ? __ldg(p.col_c + col) : 0.f;
+      pf_mean = 0.f;
+      pf_rstd = 1.f;
+      if (has_stats && row < p.M) {
         if (p.part_in != nullptr) {
-          // Chan's parallel combination of the per-64-column (mean, M2) partials the producing layer's epilogue left
+          // Chan's parallel combination of the per-32-column (mean, M2) partials the producing layer's epilogue left
           const float2* pp = reinterpret_cast<const float2*>(p.part_in) + (int64_t)row * p.npart_in;
           float msum = 0.f, m2 = 0.f;
           for (int i = 0; i < p.npart_in; ++i) msum += __ldg(&pp[i]).x;
-          mean = msum / (float)p.npart_in;
+          pf_mean = msum / (float)p.npart_in;
           for (int i = 0; i < p.npart_in; ++i) {
             const float2 q = __ldg(&pp[i]);
-            const float d = q.x - mean;
+            const float d = q.x - pf_mean;
             m2 += q.y + 32.f * d * d;
           }
-          rstd = rsqrtf(m2 / (32.f * (float)p.npart_in) + p.ln_eps);
+          pf_rstd = rsqrtf(m2 / (32.f * (float)p.npart_in) + p.ln_eps);
         } else {
-          const float2 st = *reinterpret_cast<const float2*>(p.row_stats + 2 * (int64_t)row);
-          mean = st.x;
-          rstd = st.y;
+          const float2 st = __ldg(reinterpret_cast<const float2*>(p.row_stats + 2 * (int64_t)row));
+          pf_mean = st.x;
+          pf_rstd = st.y;
         }
-        a_scale = rstd;
-        a_shift = -mean * rstd;
       }
+    };
+    prefetch_tile(unit);
+    for (int tile = unit; tile < num_tiles; tile += n_units) {
+      long long t0 = dbg ? clock64() : 0;
+      ++ntl;
+      const int m_t = tile / p.n_tiles;
+      const int n_blk = tile - m_t * p.n_tiles;
+      const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
+      const int row = m_blk * BLOCK_M + row_in_tile;
+      const bool row_ok = row < p.M;
+      const float a_scale = pf_rstd, a_shift = -pf_mean * pf_rstd;
       // ---- stage this tile's bias / col_c once (previous tile's readers are past the first barrier) ----
       named_bar_sync(1, EPI_THREADS);
       if (et < BLOCK_N) {
-        const int col = n_blk * BLOCK_N + et;
-        sBias[et] = (has_bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
-        sColc[et] = (has_stats && col < p.N) ? __ldg(p.col_c + col) : 0.f;
+        sBias[et] = pf_bias;
+        sColc[et] = pf_colc;
       }
+      prefetch_tile(tile + n_units);
       named_bar_sync(1, EPI_THREADS);
+      if (dbg) { long long t = clock64(); tk[0] += t - t0; t0 = t; }
 
       mbar_wait(&tfull_bar[abuf], aphase);
       tcgen05_fence_after();
+      if (dbg) { long long t = clock64(); tk[1] += t - t0; t0 = t; }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + abuf * BLOCK_N;
 
-      if (p.staged) {
+      if (k_staged) {
         bool released = false;
 #pragma unroll 1
         for (int q = g; q < QUARTERS; q += 2) {
@@ -358,37 +436,48 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             tmem_ld_32x32b_x32(taddr + q * QUARTER_N + hp * PANEL_N, r0);
             tmem_wait_ld();
+            if (dbg) { long long t = clock64(); tk[2] += t - t0; t0 = t; }
             // last TMEM read of this tile by this thread: hand the accumulator back early
             const bool last_q = (q + 2 >= QUARTERS) || (n_blk * BLOCK_N + (q + 2) * QUARTER_N >= p.N);
             const bool last_h = (hp == 1) || (c0 + PANEL_N >= p.N);
             if (last_q && last_h) {
               tcgen05_fence_before();
-              mbar_arrive(&tempty_bar[abuf]);
+              (PAIR ? mbar_arrive_leader(&tempty_bar[abuf]) : mbar_arrive(&tempty_bar[abuf]));
               released = true;
             }
             const int pj = qseq % EB;
             mbar_wait(&res_full_bar[g * EB + pj], (qseq / EB) & 1u);  // panel is ours (and holds the residual, if any)
+            if (dbg) { long long t = clock64(); tk[3] += t - t0; t0 = t; }
             uint8_t* erow = sE + (g * EB + pj) * EBUF_BYTES + row_in_tile * 64;
             float sh = 0.f, s1 = 0.f, s2 = 0.f;  // shifted one-pass statistics of this row's 32 outputs
+            // All shared-memory READS of the panel (residual) and of the staged vectors come first, the four 16-byte
+            // result stores last: generic smem pointers may alias as far as the compiler knows, so a store between two
+            // chunks would serialise their loads and math (measured: 1.8 k cycles per panel instead of ~0.6 k).
+            uint4 rr[4];
+            uint4* slot[4];
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+              slot[pc] = reinterpret_cast<uint4*>(erow + ((pc ^ ((row_in_tile >> 1) & 3)) << 4));  // 64-B swizzle
+              if (k_has_res) rr[pc] = *slot[pc];
+            }
+            uint4 o[4];
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r0[pc * 8 + j]);
-              epi_math8(v, sBias, sColc, q * QUARTER_N + hp * PANEL_N + pc * 8, a_scale, a_shift, has_bias, has_stats, p.act);
-              uint4* slot = reinterpret_cast<uint4*>(erow + ((pc ^ ((row_in_tile >> 1) & 3)) << 4));  // 64-B swizzle
-              if (p.residual != nullptr) {
-                const uint4 rr = *slot;
-                v[0] += bf16_lo(rr.x);
-                v[1] += bf16_hi(rr.x);
-                v[2] += bf16_lo(rr.y);
-                v[3] += bf16_hi(rr.y);
-                v[4] += bf16_lo(rr.z);
-                v[5] += bf16_hi(rr.z);
-                v[6] += bf16_lo(rr.w);
-                v[7] += bf16_hi(rr.w);
+              epi_math8(v, sBias, sColc, q * QUARTER_N + hp * PANEL_N + pc * 8, a_scale, a_shift, has_bias, has_stats, k_act);
+              if (k_has_res) {
+                v[0] += bf16_lo(rr[pc].x);
+                v[1] += bf16_hi(rr[pc].x);
+                v[2] += bf16_lo(rr[pc].y);
+                v[3] += bf16_hi(rr[pc].y);
+                v[4] += bf16_lo(rr[pc].z);
+                v[5] += bf16_hi(rr[pc].z);
+                v[6] += bf16_lo(rr[pc].w);
+                v[7] += bf16_hi(rr[pc].w);
               }
-              if (p.part_out != nullptr) {
+              if (k_part_out) {
                 if (pc == 0) sh = v[0];  // shift by the first value: keeps sum((v - sh)^2) - s1^2/n well conditioned
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -397,14 +486,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   s2 = fmaf(d, d, s2);
                 }
               }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *slot = o;
+              o[pc].x = pack_bf16x2(v[0], v[1]);
+              o[pc].y = pack_bf16x2(v[2], v[3]);
+              o[pc].z = pack_bf16x2(v[4], v[5]);
+              o[pc].w = pack_bf16x2(v[6], v[7]);
             }
-            if (p.part_out != nullptr && row_ok) {
+            if (dbg) { long long t = clock64(); tk[5] += t - t0; t0 = t; }
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) *slot[pc] = o[pc];
+            if (k_part_out && row_ok) {
               const float mq = s1 * (1.f / 32.f);
               reinterpret_cast<float2*>(p.part_out)[(int64_t)row * (p.N >> 5) + (c0 >> 5)] =
                   make_float2(sh + mq, fmaxf(s2 - s1 * mq, 0.f));
@@ -412,14 +502,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
             mbar_arrive(&e_written_bar[g * EB + pj]);
             ++qseq;
+            if (dbg) { long long t = clock64(); tk[4] += t - t0; t0 = t; }
           }
         }
         if (!released) {
           tcgen05_fence_before();
-          mbar_arrive(&tempty_bar[abuf]);
+          (PAIR ? mbar_arrive_leader(&tempty_bar[abuf]) : mbar_arrive(&tempty_bar[abuf]));
         }
-      } else {
-        // ---- direct path (fp32 output / narrow tiles): registers -> global ----
+      } else if (EPI == EPI_GENERIC) {
+        // ---- direct path (fp32 output): registers -> global ----
 #pragma unroll 1
         for (int c = g; c < BLOCK_N / 32; c += 2) {
           uint32_t r[32];
@@ -465,40 +556,68 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         tcgen05_fence_before();
-        mbar_arrive(&tempty_bar[abuf]);
+        (PAIR ? mbar_arrive_leader(&tempty_bar[abuf]) : mbar_arrive(&tempty_bar[abuf]));
       }
       abuf ^= 1u;
       if (abuf == 0) aphase ^= 1u;
     }
+    if (dbg && ntl > 0)
+      printf("gemm dbg warp %d tiles %d cycles/tile: stats+stage %lld wait_acc %lld ldtm %lld wait_panel %lld math %lld "
+             "store+fence+arrive %lld\n", warp, ntl, tk[0] / ntl, tk[1] / ntl, tk[2] / ntl, tk[3] / ntl, tk[5] / ntl, tk[4] / ntl);
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // the peer may still signal this CTA's barriers / read its smem until both are done
+  else
+    __syncthreads();
   if (warp == 2) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR)
+      tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else
+      tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int EB>
+template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                 GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES, EB>;
+  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR>;
   static bool attr_set = false;  // benign race: setting the attribute twice is harmless
   if (!attr_set) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB>,
+    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   p.n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
-  return report_cuda(cudaGetLastError(), "gemm_bf16_tn_kernel launch");
+  if (!PAIR) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+    return report_cuda(cudaGetLastError(), "gemm_bf16_tn_kernel launch");
+  }
+  // CTA pairs: cluster of 2 along x, one pair per two SMs
+  const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return report_cuda(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, tmA, tmB, tmC, tmR, p),
+                     "gemm_bf16_tn_kernel<pair> launch");
 }
 
 }  // namespace
@@ -597,7 +716,37 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   p.int_pack = intpack_override;
-  (void)cfg_override;
-  if (wide) return launch_gemm<256, 4, 2>(tmA, tmB, tmC, tmR, p, s);
-  return launch_gemm<128, 6, 2>(tmA, tmB, tmC, tmR, p, s);
+  static const int dbg_flag = []() {
+    const char* e = getenv("VLMCLIP_GEMM_DEBUG");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  p.debug = dbg_flag;
+  // CTA pairs for the wide tiles (VLMCLIP_GEMM_CFG=1 forces the single-CTA kernel for comparison)
+  const bool pair = wide && cfg_override != 1 && M > BLOCK_M;
+  // epilogue specialisation (see the EPI_* enum); anything else takes the generic instantiation
+  const bool fold = (row_stats != nullptr || stats_part_in != nullptr) && bias != nullptr;
+  int epi = EPI_GENERIC;
+  if (p.staged && cfg_override != 2) {
+    if (fold && residual == nullptr && stats_part_out == nullptr && act == 0) epi = EPI_FOLD;
+    if (fold && residual == nullptr && stats_part_out == nullptr && act == 1) epi = EPI_FOLD_ACT;
+    if (!fold && row_stats == nullptr && stats_part_in == nullptr && bias != nullptr && residual != nullptr && act == 0)
+      epi = EPI_RES;
+  }
+#define VLMCLIP_GEMM_LAUNCH(BN, ST, EBN, PR)                                                          \
+  switch (epi) {                                                                                      \
+    case EPI_FOLD: return launch_gemm<BN, ST, EBN, PR, EPI_FOLD>(tmA, tmB, tmC, tmR, p, s);          \
+    case EPI_FOLD_ACT: return launch_gemm<BN, ST, EBN, PR, EPI_FOLD_ACT>(tmA, tmB, tmC, tmR, p, s);  \
+    case EPI_RES: return launch_gemm<BN, ST, EBN, PR, EPI_RES>(tmA, tmB, tmC, tmR, p, s);            \
+    default: return launch_gemm<BN, ST, EBN, PR, EPI_GENERIC>(tmA, tmB, tmC, tmR, p, s);             \
+  }
+  if (pair) {
+    rc = make_tmap_bf16(&tmB, W, N, K, ldw, 128);  // each CTA of the pair loads 128 of the 256 W rows of a tile
+    if (rc) return rc;
+    VLMCLIP_GEMM_LAUNCH(256, 6, 2, true)
+  }
+  if (wide) {
+    VLMCLIP_GEMM_LAUNCH(256, 4, 2, false)
+  }
+  VLMCLIP_GEMM_LAUNCH(128, 6, 2, false)
+#undef VLMCLIP_GEMM_LAUNCH
 }
