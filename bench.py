@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self._stop_ev = threading.Event()
 
@@ -130,6 +130,10 @@ class ClockSampler(threading.Thread):
             }
             while not self._stop_ev.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
@@ -142,7 +146,9 @@ class ClockSampler(threading.Thread):
         self._stop_ev.set()
         self.join(timeout=2)
         med = statistics.median(self.samples) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "sm_mhz_min": min(self.samples) if self.samples else None, "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -248,9 +254,13 @@ def run_native_arm(args):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
     # ---------------- roofline of the dominant kernel (instrumented step) ----------------
+    # (towers serialised on one stream for this step only, so that a launch's event pair brackets that kernel alone)
+    overlap = model.overlap_towers
+    model.overlap_towers = False
     ops.PROFILE = {"gemm": []}
     trainer.training_step(resident[0])
     torch.cuda.synchronize()
+    model.overlap_towers = overlap
     gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.PROFILE["gemm"])
     gemm_fl = sum(f for _, _, f in ops.PROFILE["gemm"])
     n_gemm = len(ops.PROFILE["gemm"])
@@ -279,6 +289,7 @@ def run_native_arm(args):
             "step_tflops_per_gpu": step_tf / (ms_step / 1e3),
             "step_frac_of_bf16_sustained_peak": step_tf / (ms_step / 1e3) / peak_tf,
             "final_loss": final_loss,
+            "streams": "text and vision towers on two CUDA streams" if model.overlap_towers else "single stream",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -95,6 +95,9 @@ class CLIPWithAdapters(nn.Module):
         self._towers_key = None
         self._dp_group = None
         self._dp_enabled = False
+        # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
+        self.overlap_towers = os.environ.get("VLMCLIP_OVERLAP_TOWERS", "1") != "0"
+        self._side_stream = None
 
     # ------------------------------------------------------------------ reference API
     def _freeze_clip_parameters(self):
@@ -155,14 +158,18 @@ class CLIPWithAdapters(nn.Module):
 
     def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True):
         """Same contract as the reference (model_m.py:127-176): 5-key dict with the loss, 2-key dict without."""
-        if input_ids is not None and attention_mask is not None:
-            text_features = self.get_text_features(input_ids, attention_mask)
+        both = input_ids is not None and attention_mask is not None and pixel_values is not None
+        if both and self.overlap_towers and pixel_values.is_cuda:
+            text_features, image_features = self._both_towers(input_ids, attention_mask, pixel_values)
         else:
-            text_features = None
-        if pixel_values is not None:
-            image_features = self.get_image_features(pixel_values)
-        else:
-            image_features = None
+            if input_ids is not None and attention_mask is not None:
+                text_features = self.get_text_features(input_ids, attention_mask)
+            else:
+                text_features = None
+            if pixel_values is not None:
+                image_features = self.get_image_features(pixel_values)
+            else:
+                image_features = None
 
         if return_loss and text_features is not None and image_features is not None:
             scale = self._logit_scale_exp()
@@ -182,6 +189,26 @@ class CLIPWithAdapters(nn.Module):
                 "logits_per_image": logits_per_text.t(),
             }
         return {"text_features": text_features, "image_features": image_features}
+
+    def _both_towers(self, input_ids, attention_mask, pixel_values):
+        """Text branch on a side stream, vision branch on the current one, joined before the loss.
+
+        The two towers are independent until the loss (reference: model_m.py:127-150 calls them back to back).  Their
+        kernels are persistent grids of one CTA per SM, so a tower alone leaves SMs idle in the last wave of every
+        launch (the text GEMMs: 154 row tiles over 148 SMs); with two streams the other tower's next kernel takes
+        those SMs.  Autograd replays the adapter backward of each branch on the stream its forward ran on.
+        """
+        main = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=pixel_values.device)
+        side = self._side_stream
+        side.wait_stream(main)  # inputs (and the previous optimizer step) are complete
+        with torch.cuda.stream(side):
+            text_features = self.get_text_features(input_ids, attention_mask)
+        image_features = self.get_image_features(pixel_values)
+        main.wait_stream(side)
+        text_features.record_stream(main)
+        return text_features, image_features
 
     def _logit_scale_exp(self) -> float:
         # logit_scale is a frozen scalar parameter: cache exp() on the host, re-read only when it is modified
