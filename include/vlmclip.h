@@ -93,9 +93,10 @@ int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* out, int B, i
                            void* stream);
 /* Assemble vision tokens and apply pre_layrnorm (HF:211-218, HF:677):
  *   x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p]; y = LN(x).
- *   patch: fp32 [B*(S-1), D] (the patch GEMM runs with out_fp32 = 1 so the position add happens in fp32 as in
- *   the reference); cls fp32[D]; pos fp32[S,D]; y bf16 [B*S, D]. */
-int vlmclip_vision_embed_ln(const float* patch, const float* cls, const float* pos, const float* gamma,
+ *   patch: [B*(S-1), D], fp32 (patch_bf16 = 0: the patch GEMM ran with out_fp32 = 1) or bf16 (patch_bf16 = 1: the
+ *   patch GEMM's bf16 output, half the traffic; what an autocast reference run produces); the position add and the
+ *   LayerNorm are fp32 either way.  cls fp32[D]; pos fp32[S,D]; y bf16 [B*S, D]. */
+int vlmclip_vision_embed_ln(const void* patch, int patch_bf16, const float* cls, const float* pos, const float* gamma,
                             const float* beta, void* y, int B, int S, int D, float eps, void* stream);
 /* Text embeddings (HF:234-258): y[b,s] = tok[ids[b,s]] + pos[s].  ids int64 [B,S]; tok fp32[V,D]
  * or bf16 (tok_bf16=1); pos fp32 [>=S, D]; y bf16 [B*S, D].  Out-of-range ids -> return -1 is NOT possible
@@ -110,6 +111,29 @@ int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const 
  *   A query row whose keys are all masked produces zeros. */
 int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                           float scale, void* stream);
+
+/* One frozen tower, all layers, in one call: the launch sequence of towers.NativeClipTowers._encoder (the reference's
+ * CLIPEncoder loop, HF modeling_clip.py:355-386 x num_hidden_layers) issued natively.  Same kernels as the per-op
+ * entry points above; this exists because issuing ~170 ops per step from the interpreter cost more host time than the
+ * GPU needs to run them.  LayerNorm is folded: qkv_w / fc1_w hold bf16(gamma * W), qkv_b / fc1_b hold W beta + b,
+ * qkv_c / fc1_c the fold column sums (see vlmclip_gemm_bf16).
+ *   x    bf16 [B*S, D], updated in place (the residual stream); qkv bf16 [B*S, 3D], att bf16 [B*S, D],
+ *   hid  bf16 [B*S, F], stats fp32 [B*S, 2], part fp32 [B*S, D/32, 2]: workspaces.  head_dim is 64 (D = 64 H). */
+typedef struct {
+  const void* qkv_w; /* bf16 [3D, D] */
+  const float* qkv_b;
+  const float* qkv_c;
+  const void* out_w; /* bf16 [D, D] */
+  const float* out_b;
+  const void* fc1_w; /* bf16 [F, D] */
+  const float* fc1_b;
+  const float* fc1_c;
+  const void* fc2_w; /* bf16 [D, F] */
+  const float* fc2_b;
+} vlmclip_layer_t;
+int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* qkv, void* att, void* hid,
+                        float* stats, float* part, const uint8_t* key_mask, int B, int S, int H, int D, int F, float eps,
+                        int causal, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused bottleneck adapter, fp32 (trainable weights live in fp32; adapter/clip_adapter.py:4-23,131-150,

@@ -150,6 +150,11 @@ def test_im2col_and_embed(cuda, patch, dt):
     y = ops.vision_embed_ln(patch_out, cls, pos, gamma, beta, B, S)
     x = torch.cat([cls.expand(B, 1, D), patch_out.view(B, S - 1, D)], 1) + pos[None]
     assert _rel(y.view(B, S, D), O.layer_norm(x, gamma, beta)) < 4e-3
+    # bf16 patch rows (the patch GEMM's staged output): same arithmetic on the rounded input
+    p16 = patch_out.to(bf16)
+    y16 = ops.vision_embed_ln(p16, cls, pos, gamma, beta, B, S)
+    x16 = torch.cat([cls.expand(B, 1, D), p16.float().view(B, S - 1, D)], 1) + pos[None]
+    assert _rel(y16.view(B, S, D), O.layer_norm(x16, gamma, beta)) < 4e-3
 
 
 def test_text_embed(cuda):

@@ -31,9 +31,10 @@ PROTOTYPES = {
     "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),
     "vlmclip_row_stats_bf16": (_i, [_p, _i64, _p, _i, _i, _f, _p]),
     "vlmclip_im2col_patches": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
-    "vlmclip_vision_embed_ln": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "vlmclip_vision_embed_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "vlmclip_text_embed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "vlmclip_adapter_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "vlmclip_adapter_bwd_workspace": (_i64, [_i, _i, _i]),
     "vlmclip_adapter_bwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
@@ -49,6 +50,12 @@ PROTOTYPES = {
     "vlmclip_adamw_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vlmclip_gather_rows_bf16_to_f32": (_i, [_p, _i64, _p, _i, _i, _p]),
 }
+
+
+class LayerPtrs(C.Structure):
+    """vlmclip_layer_t of include/vlmclip.h: device pointers of one frozen encoder layer (LayerNorm folded)."""
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_w", "qkv_b", "qkv_c", "out_w", "out_b", "fc1_w", "fc1_b", "fc1_c",
+                                           "fc2_w", "fc2_b")]
 
 
 class NativeError(RuntimeError):

@@ -1,0 +1,44 @@
+// Native launch sequence of one frozen CLIP tower (HF modeling_clip.py:355-386 CLIPEncoderLayer x L), LayerNorm folded
+// into the following GEMM.  The kernels are the ones the per-op entry points launch; this entry point only removes
+// the host-side cost of issuing them one by one from Python (about 50 us per op, 170 ops per step: the interpreter
+// was slower than the GPU), so the frozen towers are two calls per step.
+#include "../../include/vlmclip.h"
+#include "common.cuh"
+
+extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* qkv, void* att, void* hid,
+                                   float* stats, float* part, const uint8_t* key_mask, int B, int S, int H, int D, int F,
+                                   float eps, int causal, int act, void* stream) {
+  using namespace vlmclip;
+  VLMCLIP_CHECK_ARG(layers && n_layers > 0 && x && qkv && att && hid && stats && part, "encoder_fwd: null pointer");
+  VLMCLIP_CHECK_ARG(B > 0 && S > 0 && H > 0 && D == H * 64 && F > 0 && D % 32 == 0, "encoder_fwd: bad dims");
+  const int M = B * S;
+  const int npart = D / 32;
+  const float scale = 0.125f;  // head_dim 64
+  int rc = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const vlmclip_layer_t& L = layers[l];
+    // LN1 statistics of the residual stream: explicit pass for the first layer (the embedding kernels emit no
+    // partials), otherwise the combine of the per-32-column partials the previous fc2 epilogue left
+    rc = l == 0 ? vlmclip_row_stats_bf16(x, D, stats, M, D, eps, stream)
+                : vlmclip_ln_partials_to_stats(part, stats, M, npart, eps, stream);
+    if (rc) return rc;
+    rc = vlmclip_gemm_bf16(x, D, L.qkv_w, D, qkv, 3 * (int64_t)D, L.qkv_b, nullptr, 0, stats, L.qkv_c, nullptr, 0, eps,
+                           nullptr, M, 3 * D, D, VLMCLIP_ACT_NONE, 0, stream);
+    if (rc) return rc;
+    rc = vlmclip_attention_fwd(qkv, att, key_mask, B, S, H, causal, scale, stream);
+    if (rc) return rc;
+    // x += out_proj(att), in place; the epilogue leaves the LN2 partials
+    rc = vlmclip_gemm_bf16(att, D, L.out_w, D, x, D, L.out_b, x, D, nullptr, nullptr, nullptr, 0, eps, part, M, D, D,
+                           VLMCLIP_ACT_NONE, 0, stream);
+    if (rc) return rc;
+    rc = vlmclip_ln_partials_to_stats(part, stats, M, npart, eps, stream);
+    if (rc) return rc;
+    rc = vlmclip_gemm_bf16(x, D, L.fc1_w, D, hid, F, L.fc1_b, nullptr, 0, stats, L.fc1_c, nullptr, 0, eps, nullptr, M, F,
+                           D, act, 0, stream);
+    if (rc) return rc;
+    rc = vlmclip_gemm_bf16(hid, F, L.fc2_w, F, x, D, L.fc2_b, x, D, nullptr, nullptr, nullptr, 0, eps, part, M, D, F,
+                           VLMCLIP_ACT_NONE, 0, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}

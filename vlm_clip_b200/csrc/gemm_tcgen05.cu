@@ -134,7 +134,8 @@ __device__ __forceinline__ void epi_math8(float* v, const float* sBias, const fl
 //   EPI_FOLD      LN fold + bias                     (QKV)
 //   EPI_FOLD_ACT  LN fold + bias + quick_gelu        (fc1)
 //   EPI_RES       bias + residual + LN partials out  (out-proj, fc2)
-enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3 };
+//   EPI_PLAIN     bf16 store only                    (patch embedding)
+enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3, EPI_PLAIN = 4 };
 
 template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -166,7 +167,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // epilogue switches: compile-time constants for the specialised instantiations
   const bool k_staged = EPI == EPI_GENERIC ? p.staged != 0 : true;
   const bool k_has_res = EPI == EPI_GENERIC ? p.residual != nullptr : EPI == EPI_RES;
-  const bool k_has_bias = EPI == EPI_GENERIC ? p.bias != nullptr : true;
+  const bool k_has_bias = EPI == EPI_GENERIC ? p.bias != nullptr : EPI != EPI_PLAIN;
   const bool k_has_stats = EPI == EPI_GENERIC ? (p.row_stats != nullptr || p.part_in != nullptr)
                                               : (EPI == EPI_FOLD || EPI == EPI_FOLD_ACT);
   const bool k_part_out = EPI == EPI_GENERIC ? p.part_out != nullptr : (EPI == EPI_RES && p.part_out != nullptr);
@@ -731,12 +732,16 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     if (fold && residual == nullptr && stats_part_out == nullptr && act == 1) epi = EPI_FOLD_ACT;
     if (!fold && row_stats == nullptr && stats_part_in == nullptr && bias != nullptr && residual != nullptr && act == 0)
       epi = EPI_RES;
+    if (!fold && row_stats == nullptr && stats_part_in == nullptr && bias == nullptr && residual == nullptr &&
+        stats_part_out == nullptr && act == 0)
+      epi = EPI_PLAIN;
   }
 #define VLMCLIP_GEMM_LAUNCH(BN, ST, EBN, PR)                                                          \
   switch (epi) {                                                                                      \
     case EPI_FOLD: return launch_gemm<BN, ST, EBN, PR, EPI_FOLD>(tmA, tmB, tmC, tmR, p, s);          \
     case EPI_FOLD_ACT: return launch_gemm<BN, ST, EBN, PR, EPI_FOLD_ACT>(tmA, tmB, tmC, tmR, p, s);  \
     case EPI_RES: return launch_gemm<BN, ST, EBN, PR, EPI_RES>(tmA, tmB, tmC, tmR, p, s);            \
+    case EPI_PLAIN: return launch_gemm<BN, ST, EBN, PR, EPI_PLAIN>(tmA, tmB, tmC, tmR, p, s);        \
     default: return launch_gemm<BN, ST, EBN, PR, EPI_GENERIC>(tmA, tmB, tmC, tmR, p, s);             \
   }
   if (pair) {

@@ -195,9 +195,10 @@ im2col_pad_kernel(__nv_bfloat16* __restrict__ out, int64_t rows, int K, int Kpad
 }
 
 // vision tokens: x[b,0] = cls + pos[0]; x[b,1+q] = patch[b,q] + pos[1+q]; y = LN(x)
-template <int NV>
+// patch rows are fp32 (PATCH_BF16 = false) or bf16 (the patch GEMM's staged bf16 output: half the traffic)
+template <int NV, bool PATCH_BF16>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+vision_embed_ln_kernel(const void* __restrict__ patch_v, const float* __restrict__ cls,
                        const float* __restrict__ pos, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int B, int S, int D,
                        float eps) {
@@ -207,7 +208,9 @@ vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict_
   const int s = (int)(row % S);
   const int64_t b = row / S;
   const int nvec = D >> 3;
-  const float* src = (s == 0) ? cls : patch + (b * (S - 1) + (s - 1)) * (int64_t)D;
+  const int64_t prow = (b * (S - 1) + (s - 1)) * (int64_t)D;
+  const float* src = (s == 0 || PATCH_BF16) ? cls : reinterpret_cast<const float*>(patch_v) + prow;
+  const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(patch_v) + prow;
   const float* pr = pos + (int64_t)s * D;
   float v[NV][8];
   int valid[NV];
@@ -216,8 +219,15 @@ vision_embed_ln_kernel(const float* __restrict__ patch, const float* __restrict_
     const int vi = lane + i * 32;
     valid[i] = vi < nvec;
     if (valid[i]) {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(src + vi * 8));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(src + vi * 8 + 4));
+      float4 a0, a1;
+      if (PATCH_BF16 && s != 0) {
+        const uint4 raw = ld_nc_v4(src16 + vi * 8);
+        a0 = make_float4(bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y));
+        a1 = make_float4(bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w));
+      } else {
+        a0 = __ldg(reinterpret_cast<const float4*>(src + vi * 8));
+        a1 = __ldg(reinterpret_cast<const float4*>(src + vi * 8 + 4));
+      }
       const float4 p0 = __ldg(reinterpret_cast<const float4*>(pr + vi * 8));
       const float4 p1 = __ldg(reinterpret_cast<const float4*>(pr + vi * 8 + 4));
       v[i][0] = a0.x + p0.x;
@@ -416,8 +426,9 @@ extern "C" int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* ou
   return report_cuda(cudaGetLastError(), "im2col_kernel launch");
 }
 
-extern "C" int vlmclip_vision_embed_ln(const float* patch, const float* cls, const float* pos, const float* gamma,
-                                       const float* beta, void* y, int B, int S, int D, float eps, void* stream) {
+extern "C" int vlmclip_vision_embed_ln(const void* patch, int patch_bf16, const float* cls, const float* pos,
+                                       const float* gamma, const float* beta, void* y, int B, int S, int D, float eps,
+                                       void* stream) {
   VLMCLIP_CHECK_ARG(patch && cls && pos && gamma && beta && y, "vision_embed_ln: null pointer");
   VLMCLIP_CHECK_ARG(B > 0 && S > 1 && D % 8 == 0 && D <= MAX_VEC * 256, "vision_embed_ln: bad dims B=%d S=%d D=%d", B, S, D);
   VLMCLIP_CHECK_ARG((uintptr_t)patch % 16 == 0 && (uintptr_t)cls % 16 == 0 && (uintptr_t)pos % 16 == 0 &&
@@ -426,8 +437,13 @@ extern "C" int vlmclip_vision_embed_ln(const float* patch, const float* cls, con
   const int64_t rows = (int64_t)B * S;
   const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   count_launch(1);
-  VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-                             patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
+  if (patch_bf16) {
+    VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV, true><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
+  } else {
+    VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV, false><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
+  }
   return report_cuda(cudaGetLastError(), "vision_embed_ln_kernel launch");
 }
 

@@ -51,6 +51,7 @@ class DevicePrefetcher:
                 queue.append(self._stage(next(it)))
             except StopIteration:
                 pass
+            batch["inputs_ready"] = ev  # lets the frozen towers start without waiting for the consumer's stream
             yield batch
 
 

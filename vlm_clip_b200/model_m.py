@@ -97,7 +97,7 @@ class CLIPWithAdapters(nn.Module):
         self._dp_enabled = False
         # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
         self.overlap_towers = os.environ.get("VLMCLIP_OVERLAP_TOWERS", "1") != "0"
-        self._side_stream = None
+        self._tower_streams = None
 
     # ------------------------------------------------------------------ reference API
     def _freeze_clip_parameters(self):
@@ -120,6 +120,7 @@ class CLIPWithAdapters(nn.Module):
         if self._towers is None or self._towers_key != key:
             self._towers = NativeClipTowers(self.clip, p.device)
             self._towers_key = key
+            torch.cuda.current_stream().synchronize()  # packed weights are read from the private tower streams
         return self._towers
 
     def refresh_backbone(self):
@@ -137,8 +138,10 @@ class CLIPWithAdapters(nn.Module):
             # raise through the adapter so the message names the missing kernel
             self.shared_adapters[0](None, None)
         bb = self._backbone()
-        B, S = input_ids.shape
         hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
+        return self._text_head(bb, hidden, input_ids.shape[0], input_ids.shape[1])
+
+    def _text_head(self, bb, hidden, B, S):
         # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32
         tok0 = ops.layernorm_rows_f32(hidden, bb.final_ln_w, bb.final_ln_b, bb.eps_t, rows=B, ldx=S * bb.Dt)
         if self.use_text_adapter:
@@ -148,19 +151,21 @@ class CLIPWithAdapters(nn.Module):
     def get_image_features(self, pixel_values):
         """Image features with adapter: fp32 [B, P] (reference: model_m.py:107-125)."""
         bb = self._backbone()
-        B = pixel_values.shape[0]
         hidden = bb.vision_hidden(pixel_values)  # bf16 [B*S, Dv], pre post_layernorm
+        return self._image_head(bb, hidden, pixel_values.shape[0])
+
+    def _image_head(self, bb, hidden, B):
         if self.use_vision_adapter:
             cls = self.vision_adapter.forward_token0(hidden, B, bb.Sv)
         else:
             cls = ops.gather_rows_f32(hidden, B, bb.Sv * bb.Dv, bb.Dv)
         return ops.linear_f32(cls, bb.visual_projection)
 
-    def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True):
+    def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True, *, inputs_ready=None):
         """Same contract as the reference (model_m.py:127-176): 5-key dict with the loss, 2-key dict without."""
         both = input_ids is not None and attention_mask is not None and pixel_values is not None
         if both and self.overlap_towers and pixel_values.is_cuda:
-            text_features, image_features = self._both_towers(input_ids, attention_mask, pixel_values)
+            text_features, image_features = self._both_towers(input_ids, attention_mask, pixel_values, inputs_ready)
         else:
             if input_ids is not None and attention_mask is not None:
                 text_features = self.get_text_features(input_ids, attention_mask)
@@ -190,24 +195,43 @@ class CLIPWithAdapters(nn.Module):
             }
         return {"text_features": text_features, "image_features": image_features}
 
-    def _both_towers(self, input_ids, attention_mask, pixel_values):
-        """Text branch on a side stream, vision branch on the current one, joined before the loss.
+    def _both_towers(self, input_ids, attention_mask, pixel_values, inputs_ready=None):
+        """Frozen towers on two private streams, adapters / projections on the caller's stream.
 
-        The two towers are independent until the loss (reference: model_m.py:127-150 calls them back to back).  Their
-        kernels are persistent grids of one CTA per SM, so a tower alone leaves SMs idle in the last wave of every
-        launch (the text GEMMs: 154 row tiles over 148 SMs); with two streams the other tower's next kernel takes
-        those SMs.  Autograd replays the adapter backward of each branch on the stream its forward ran on.
+        The towers are independent of each other until the loss (reference: model_m.py:127-150 calls them back to
+        back) and, being frozen, independent of the optimizer.  Their kernels are persistent grids of one CTA per SM,
+        so a tower alone leaves SMs idle in the last wave of every launch; with two streams the other tower's next
+        kernel takes those SMs.  `inputs_ready` (an extension: a CUDA event after which the inputs are complete, e.g.
+        `DevicePrefetcher`'s copy event) lets the towers of step i+1 start while the caller's stream still runs the
+        latency-bound adapter backward / AdamW of step i; without it they wait for the caller's stream.
         """
+        if self.use_shared_adapters:
+            self.shared_adapters[0](None, None)
+        bb = self._backbone()
         main = torch.cuda.current_stream()
-        if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=pixel_values.device)
-        side = self._side_stream
-        side.wait_stream(main)  # inputs (and the previous optimizer step) are complete
-        with torch.cuda.stream(side):
-            text_features = self.get_text_features(input_ids, attention_mask)
-        image_features = self.get_image_features(pixel_values)
-        main.wait_stream(side)
-        text_features.record_stream(main)
+        if self._tower_streams is None:
+            dev = pixel_values.device
+            self._tower_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        vis, txt = self._tower_streams
+        for st in (vis, txt):
+            if inputs_ready is not None:
+                st.wait_event(inputs_ready)
+            else:
+                st.wait_stream(main)
+        with torch.cuda.stream(txt):
+            t_hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)
+        with torch.cuda.stream(vis):
+            v_hidden = bb.vision_hidden(pixel_values)
+        input_ids.record_stream(txt)
+        if attention_mask is not None:
+            attention_mask.record_stream(txt)
+        pixel_values.record_stream(vis)
+        main.wait_stream(txt)
+        main.wait_stream(vis)
+        t_hidden.record_stream(main)
+        v_hidden.record_stream(main)
+        text_features = self._text_head(bb, t_hidden, input_ids.shape[0], input_ids.shape[1])
+        image_features = self._image_head(bb, v_hidden, pixel_values.shape[0])
         return text_features, image_features
 
     def _logit_scale_exp(self) -> float:

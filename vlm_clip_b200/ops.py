@@ -147,14 +147,14 @@ def im2col(pixels, patch: int, out=None):
 
 
 @_traced
-def vision_embed_ln(patch_f32, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
+def vision_embed_ln(patch, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
     D = pos.shape[1]
-    _req(patch_f32.dtype == f32 and patch_f32.shape == (B * (S - 1), D) and patch_f32.is_contiguous(),
-         "vision_embed_ln: patch must be fp32 [B*(S-1), D]")
+    _req(patch.dtype in (f32, bf16) and patch.shape == (B * (S - 1), D) and patch.is_contiguous(),
+         "vision_embed_ln: patch must be fp32 or bf16 [B*(S-1), D]")
     if out is None:
         out = torch.empty((B * S, D), device=pos.device, dtype=bf16)
     N.check(
-        N.load().vlmclip_vision_embed_ln(N.ptr(patch_f32), N.ptr(cls), N.ptr(pos), N.ptr(gamma), N.ptr(beta),
+        N.load().vlmclip_vision_embed_ln(N.ptr(patch), 1 if patch.dtype == bf16 else 0, N.ptr(cls), N.ptr(pos), N.ptr(gamma), N.ptr(beta),
                                          N.ptr(out), B, S, D, float(eps), N.stream()), "vlmclip_vision_embed_ln")
     return out
 

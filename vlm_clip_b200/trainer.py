@@ -95,6 +95,7 @@ class CLIPAdapterTrainer:
             attention_mask=batch.get("attention_mask"),
             pixel_values=batch.get("pixel_values"),
             return_loss=True,
+            inputs_ready=batch.get("inputs_ready"),
         )
         loss = outputs["loss"]
         opt = self.optimizer
