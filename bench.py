@@ -102,7 +102,7 @@ def run_reference_arm(args):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -312,12 +312,27 @@ def run_native_arm(args):
         base, _ = cpu_reference_step_rate(steps=3, warmup=1)
         line["cpu_baseline"] = base
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner under
+    # torchrun, for one) is sent to stderr by pointing fd 1 at fd 2 and keeping a private handle on the real stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)  # ~1.2 s timed: long enough to sit at the sustained (power-capped) clock
