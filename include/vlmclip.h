@@ -91,6 +91,19 @@ int vlmclip_row_stats_bf16(const void* x, int64_t ldx, float* stats_out, int M, 
  *   = c*p*p + i*p + j (matches patch_embedding.weight.view(D,-1), which the caller pads the same way). */
 int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* out, int B, int H, int W, int patch,
                            void* stream);
+/* Frame preprocessing fused with patch extraction (process_video.py:14-29 + HF:209): decoded uint8 HWC frames ->
+ * (BGR2RGB) -> bilinear resize with OpenCV's 11-bit fixed-point arithmetic -> /255 -> (x - mean) / std -> bf16 im2col
+ * rows in the layout of vlmclip_im2col_patches.  frames: n_frames images of [Hs, Ws, 3] uint8, frame_stride bytes
+ * apart (any clip / frame nesting that is a constant stride).  ytab [H][3] / xtab [W][3] int32 device tables
+ * (source index, weight of it, weight of the next; weights sum to 2048) select the resize; NULL for both = frames
+ * are already H x W.  mean / std are per output channel (RGB order). */
+int vlmclip_preprocess_patches(const uint8_t* frames, int64_t frame_stride, int Hs, int Ws, int bgr, const int32_t* ytab,
+                               const int32_t* xtab, float mean0, float mean1, float mean2, float std0, float std1,
+                               float std2, void* out, int n_frames, int H, int W, int patch, void* stream);
+/* Temporal mean-pool of per-frame features (not in the reference, defined as
+ * get_image_features(frames).view(B, T, P).mean(1)): y[b] = mean_t x[b*T + t]; and its backward dx = dy / T. */
+int vlmclip_mean_pool(const float* x, float* y, int B, int T, int P, void* stream);
+int vlmclip_mean_pool_bwd(const float* dy, float* dx, int B, int T, int P, void* stream);
 /* Assemble vision tokens and apply pre_layrnorm (HF:211-218, HF:677):
  *   x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p]; y = LN(x).
  *   patch: [B*(S-1), D], fp32 (patch_bf16 = 0: the patch GEMM ran with out_fp32 = 1) or bf16 (patch_bf16 = 1: the

@@ -435,3 +435,36 @@ def test_fused_adamw_matches_torch(cuda):
         assert abs(opt.grad_norm.item() - norm.item()) < 1e-4 * max(1.0, norm.item())
         for p, q in zip(ps, qs):
             assert torch.allclose(p, q, atol=1e-7, rtol=1e-5)
+
+
+@pytest.mark.parametrize("hs,ws,h,patch,bgr", [(60, 80, 32, 16, False), (32, 32, 32, 16, True), (45, 61, 28, 14, False)])
+def test_preprocess_patches_bit_exact(cuda, hs, ws, h, patch, bgr):
+    """uint8 frames -> resize -> /255 -> normalise -> bf16 im2col: integer resize + IEEE float ops, so bit exact against
+    the numpy oracle (which is itself pinned against cv2)."""
+    import numpy as np
+
+    from oracle import preprocess_oracle as P
+    from vlm_clip_b200 import ops
+
+    rng = np.random.default_rng(hs * 7 + ws)
+    frames = rng.integers(0, 256, (2, 3, hs, ws, 3), dtype=np.uint8)  # [clips, T, Hs, Ws, 3]
+    cols = ops.preprocess_patches(torch.from_numpy(frames).to(cuda), h, h, patch, P.IMAGENET_MEAN, P.IMAGENET_STD, bgr)
+    pix = P.preprocess_frames(frames.reshape(-1, hs, ws, 3), h, h, P.IMAGENET_MEAN, P.IMAGENET_STD, bgr)
+    ref = torch.from_numpy(P.patches(pix, patch)).to(bf16)
+    K = 3 * patch * patch
+    assert cols.shape == (6 * (h // patch) ** 2, (K + 63) // 64 * 64)
+    assert torch.equal(cols[:, :K].cpu(), ref)
+    assert (cols[:, K:] == 0).all()
+
+
+def test_mean_pool_fwd_bwd(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(11)
+    x = torch.randn(6 * 5, 48, device=cuda, generator=g, requires_grad=True)
+    y = ops.mean_pool(x, 5)
+    ref = x.detach().view(6, 5, 48).mean(1)
+    assert torch.allclose(y, ref, atol=1e-6)
+    dy = torch.randn(6, 48, device=cuda, generator=g)
+    y.backward(dy)
+    assert torch.allclose(x.grad, (dy / 5)[:, None, :].expand(6, 5, 48).reshape(30, 48), atol=1e-7)

@@ -199,3 +199,38 @@ def test_model_errors_and_api(cuda, clip_b32):
     assert set(out) == {"text_features", "image_features"} and out["image_features"].shape == (2, 512)
     with pytest.raises(ValueError):
         m2.get_image_features(torch.zeros(1, 3, 128, 128, device=cuda))
+
+
+def test_video_clips_and_uint8_frames(cuda, clip_b32, sd_b32):
+    """SURVEY.md 8a-12 (config 4): clip feature = mean over frames of get_image_features; decoded uint8 frames give the
+    same result as the float pixels the CPU preprocessing (oracle, pinned on cv2) produces from them."""
+    import numpy as np
+
+    from oracle import preprocess_oracle as P
+
+    model = _make_model(cuda, clip_b32)
+    model.eval()
+    model.pixel_mean, model.pixel_std = P.IMAGENET_MEAN, P.IMAGENET_STD  # process_video.py:24
+    rng = np.random.default_rng(5)
+    B, T = 2, 3
+    frames = rng.integers(0, 256, (B, T, 120, 160, 3), dtype=np.uint8)
+    pix = P.preprocess_frames(frames.reshape(-1, 120, 160, 3), 224, 224, P.IMAGENET_MEAN, P.IMAGENET_STD)  # [B*T,3,224,224]
+    clips = torch.from_numpy(pix).view(B, T, 3, 224, 224).permute(0, 2, 1, 3, 4).contiguous().to(cuda)  # [B,3,T,H,W]
+    with torch.no_grad():
+        per_frame = model.get_image_features(torch.from_numpy(pix).to(cuda))
+        v_float = model.get_video_features(clips)
+        v_u8 = model.get_video_features(torch.from_numpy(frames).to(cuda))
+        f_u8 = model.get_image_features(torch.from_numpy(frames[0]).to(cuda))
+    assert torch.allclose(v_float, per_frame.view(B, T, -1).mean(1), atol=1e-6)
+    assert torch.equal(v_u8, v_float)            # same bf16 im2col bits -> identical features
+    assert torch.equal(f_u8, per_frame[:T])
+    # against the fp32 oracle of the per-frame path
+    ta, va = _adapters_sd(model)
+    ref = O.model_m_image_features(sd_b32, 12, torch.from_numpy(pix).to(cuda), va) if hasattr(O, "model_m_image_features") else None
+    if ref is not None:
+        assert _rel(v_float, ref.view(B, T, -1).mean(1)) < FEAT_TOL
+    # forward() with clips: loss over clip-level features
+    ids = torch.randint(3, 49406, (B, 77), device=cuda)
+    ids[:, 0] = torch.tensor([5, 42], device=cuda)
+    out = model(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=torch.from_numpy(frames).to(cuda))
+    assert out["logits_per_image"].shape == (B, B) and torch.isfinite(out["loss"])

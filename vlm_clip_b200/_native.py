@@ -31,6 +31,9 @@ PROTOTYPES = {
     "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),
     "vlmclip_row_stats_bf16": (_i, [_p, _i64, _p, _i, _i, _f, _p]),
     "vlmclip_im2col_patches": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
+    "vlmclip_preprocess_patches": (_i, [_p, _i64, _i, _i, _i, _p, _p, _f, _f, _f, _f, _f, _f, _p, _i, _i, _i, _i, _p]),
+    "vlmclip_mean_pool": (_i, [_p, _p, _i, _i, _i, _p]),
+    "vlmclip_mean_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p]),
     "vlmclip_vision_embed_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "vlmclip_text_embed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),

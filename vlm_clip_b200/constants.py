@@ -37,3 +37,7 @@ _WORDS = {"angry": "angry", "disgust": "disgusted", "fear": "afraid", "happy": "
 def get_emotion_descriptions():
     """Five prompts per RAF-DB class (same structure as reference constants.py:20-75: 7 classes x 5 prompts)."""
     return {e: [t.format(_WORDS[e]) for t in _TEMPLATES] for e in EMOTIONS}
+
+# pixel normalisation constants (RGB): process_video.py:24 uses ImageNet's; CLIPImageProcessor uses CLIP's
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)

@@ -29,6 +29,7 @@ import torch.nn as nn
 from . import _native as N
 from . import ops
 from .adapter.clip_adapter import SharedMHSAttentionAdapter, TextAdapter, VisionAdapter
+from .constants import CLIP_MEAN, CLIP_STD
 from .towers import NativeClipTowers
 
 
@@ -98,6 +99,8 @@ class CLIPWithAdapters(nn.Module):
         # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
         self.overlap_towers = os.environ.get("VLMCLIP_OVERLAP_TOWERS", "1") != "0"
         self._tower_streams = None
+        # on-GPU preprocessing of uint8 frames (extension): CLIP's normalisation by default, RGB channel order
+        self.pixel_mean, self.pixel_std, self.frames_bgr = CLIP_MEAN, CLIP_STD, False
 
     # ------------------------------------------------------------------ reference API
     def _freeze_clip_parameters(self):
@@ -149,10 +152,36 @@ class CLIPWithAdapters(nn.Module):
         return ops.linear_f32(tok0, bb.text_projection)
 
     def get_image_features(self, pixel_values):
-        """Image features with adapter: fp32 [B, P] (reference: model_m.py:107-125)."""
+        """Image features with adapter: fp32 [B, P] (reference: model_m.py:107-125).
+
+        `pixel_values`: float [B, 3, H, W] as in the reference, or (extension) decoded uint8 frames [B, Hs, Ws, 3], which
+        are resized / scaled / normalised on the GPU (`self.pixel_mean`, `self.pixel_std`, `self.frames_bgr`)."""
         bb = self._backbone()
-        hidden = bb.vision_hidden(pixel_values)  # bf16 [B*S, Dv], pre post_layernorm
-        return self._image_head(bb, hidden, pixel_values.shape[0])
+        hidden, n = self._vision_hidden(bb, pixel_values)
+        return self._image_head(bb, hidden, n)
+
+    def get_video_features(self, clips):
+        """Clip features: fp32 [B, P] = get_image_features(frames).view(B, T, P).mean(1) (the reference
+        stops at `process_video`, no model consumes its output).  `clips`: float [B, 3, T, H, W] (stacked
+        `process_video` outputs, process_video.py:29) or decoded uint8 frames [B, T, Hs, Ws, 3]."""
+        if clips.dim() != 5:
+            raise ValueError("clips must be [B, 3, T, H, W] float or [B, T, Hs, Ws, 3] uint8")
+        T = clips.shape[1] if clips.dtype == torch.uint8 else clips.shape[2]
+        bb = self._backbone()
+        hidden, n = self._vision_hidden(bb, clips)
+        return ops.mean_pool(self._image_head(bb, hidden, n), T)
+
+    def _vision_hidden(self, bb, pixel_values):
+        """Tower output for any accepted pixel layout -> (bf16 [n*S, D], n images)."""
+        if pixel_values.dtype == torch.uint8:
+            if pixel_values.dim() not in (4, 5) or pixel_values.shape[-1] != 3:
+                raise ValueError("uint8 frames must be [B, Hs, Ws, 3] or [B, T, Hs, Ws, 3]")
+            n = pixel_values.numel() // (pixel_values.shape[-3] * pixel_values.shape[-2] * 3)
+            return bb.vision_hidden_u8(pixel_values, self.pixel_mean, self.pixel_std, self.frames_bgr), n
+        if pixel_values.dim() == 5:  # [B, 3, T, H, W] -> [B*T, 3, H, W] (a layout copy, as the reference's caller would do)
+            B, C, T, H, W = pixel_values.shape
+            pixel_values = pixel_values.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+        return bb.vision_hidden(pixel_values), pixel_values.shape[0]
 
     def _image_head(self, bb, hidden, B):
         if self.use_vision_adapter:
@@ -172,7 +201,8 @@ class CLIPWithAdapters(nn.Module):
             else:
                 text_features = None
             if pixel_values is not None:
-                image_features = self.get_image_features(pixel_values)
+                image_features = (self.get_video_features(pixel_values) if pixel_values.dim() == 5
+                                  else self.get_image_features(pixel_values))
             else:
                 image_features = None
 
@@ -221,7 +251,7 @@ class CLIPWithAdapters(nn.Module):
         with torch.cuda.stream(txt):
             t_hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)
         with torch.cuda.stream(vis):
-            v_hidden = bb.vision_hidden(pixel_values)
+            v_hidden, n_img = self._vision_hidden(bb, pixel_values)
         input_ids.record_stream(txt)
         if attention_mask is not None:
             attention_mask.record_stream(txt)
@@ -231,7 +261,9 @@ class CLIPWithAdapters(nn.Module):
         t_hidden.record_stream(main)
         v_hidden.record_stream(main)
         text_features = self._text_head(bb, t_hidden, input_ids.shape[0], input_ids.shape[1])
-        image_features = self._image_head(bb, v_hidden, pixel_values.shape[0])
+        image_features = self._image_head(bb, v_hidden, n_img)
+        if pixel_values.dim() == 5:  # clips: temporal mean-pool of the per-frame features
+            image_features = ops.mean_pool(image_features, n_img // pixel_values.shape[0])
         return text_features, image_features
 
     def _logit_scale_exp(self) -> float:

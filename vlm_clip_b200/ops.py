@@ -146,6 +146,84 @@ def im2col(pixels, patch: int, out=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------ preprocessing
+_RESIZE_TABLES = {}
+
+
+def _linear_coeffs(src: int, dst: int):
+    """Source index and the two 11-bit weights of every destination index: OpenCV's INTER_LINEAR coefficient rule
+    (resize.cpp: fx = (float)((dx + 0.5) * scale - 0.5); clamp; cvRound(w * 2048)), float32 arithmetic as there."""
+    import numpy as np
+
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * (src / dst) - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    lo, hi = s < 0, s >= src - 1
+    s = np.where(lo, 0, np.where(hi, src - 1, s))
+    f = np.where(lo | hi, np.float32(0), f).astype(np.float32)
+    w0 = np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int32)
+    w1 = np.rint(f * np.float32(2048)).astype(np.int32)
+    return np.stack([s.astype(np.int32), w0, w1], 1)
+
+
+def resize_tables(Hs: int, Ws: int, H: int, W: int, device):
+    """Device copies of the row / column coefficient tables for an Hs x Ws -> H x W bilinear resize (cached)."""
+    key = (Hs, Ws, H, W, str(device))
+    t = _RESIZE_TABLES.get(key)
+    if t is None:
+        t = (torch.from_numpy(_linear_coeffs(Hs, H)).to(device), torch.from_numpy(_linear_coeffs(Ws, W)).to(device))
+        _RESIZE_TABLES[key] = t
+    return t
+
+
+@_traced
+def preprocess_patches(frames_u8, H: int, W: int, patch: int, mean, std, bgr: bool = False, out=None):
+    """uint8 [..., Hs, Ws, 3] decoded frames -> bf16 im2col rows [n*(H/p)*(W/p), Kpad] (resize, /255, normalise fused)."""
+    _req(frames_u8.dtype == torch.uint8 and frames_u8.dim() >= 3 and frames_u8.shape[-1] == 3 and frames_u8.is_contiguous(),
+         "preprocess_patches: frames must be contiguous uint8 [..., Hs, Ws, 3]")
+    Hs, Ws = int(frames_u8.shape[-3]), int(frames_u8.shape[-2])
+    n = frames_u8.numel() // (Hs * Ws * 3)
+    K = 3 * patch * patch
+    Kpad = (K + 63) // 64 * 64
+    rows = n * (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty((rows, Kpad), device=frames_u8.device, dtype=bf16)
+    ytab = xtab = None
+    if (Hs, Ws) != (H, W):
+        ytab, xtab = resize_tables(Hs, Ws, H, W, frames_u8.device)
+    N.check(
+        N.load().vlmclip_preprocess_patches(N.ptr(frames_u8), Hs * Ws * 3, Hs, Ws, 1 if bgr else 0, N.ptr(ytab), N.ptr(xtab),
+                                            float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]),
+                                            float(std[2]), N.ptr(out), n, H, W, patch, N.stream()),
+        "vlmclip_preprocess_patches")
+    return out
+
+
+class _MeanPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, T):
+        _req(x.dtype == f32 and x.dim() == 2 and x.is_contiguous() and x.shape[0] % T == 0, "mean_pool: x must be fp32 [B*T, P]")
+        B, P = x.shape[0] // T, x.shape[1]
+        y = torch.empty((B, P), device=x.device, dtype=f32)
+        N.check(N.load().vlmclip_mean_pool(N.ptr(x), N.ptr(y), B, T, P, N.stream()), "vlmclip_mean_pool")
+        ctx.dims = (B, T, P)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, P = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.empty((B * T, P), device=dy.device, dtype=f32)
+        N.check(N.load().vlmclip_mean_pool_bwd(N.ptr(dy), N.ptr(dx), B, T, P, N.stream()), "vlmclip_mean_pool_bwd")
+        return dx, None
+
+
+def mean_pool(x, T: int):
+    """[B*T, P] -> [B, P]: mean over the T consecutive rows of each clip."""
+    return _MeanPool.apply(x, int(T))
+
+
 @_traced
 def vision_embed_ln(patch, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
     D = pos.shape[1]

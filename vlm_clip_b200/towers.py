@@ -219,10 +219,23 @@ class NativeClipTowers:
             pixel_values = pixel_values.float()
         pixel_values = pixel_values.contiguous()
         B = pixel_values.shape[0]
-        cols = ops.im2col(pixel_values, self.patch)
+        return self._vision_from_cols(ops.im2col(pixel_values, self.patch), B)
+
+    def _vision_from_cols(self, cols: torch.Tensor, B: int) -> torch.Tensor:
         patches = ops.gemm(cols, self.patch_w)  # [B*np, D] bf16 (staged TMA epilogue; the fp32 path costs 2x the traffic)
         x = ops.vision_embed_ln(patches, self.cls, self.pos_v, self.pre_ln_w, self.pre_ln_b, B, self.Sv, self.eps_v)
         return self._encoder(x, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None)
+
+    @torch.no_grad()
+    def vision_hidden_u8(self, frames_u8: torch.Tensor, mean, std, bgr: bool = False) -> torch.Tensor:
+        """Same as `vision_hidden`, from decoded uint8 frames [..., Hs, Ws, 3]: resize to the model resolution, /255 and
+        normalisation are fused into the patch extraction (process_video.py:14-29 semantics; `vlmclip_preprocess_patches`)."""
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() < 4 or frames_u8.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [..., Hs, Ws, 3]")
+        frames_u8 = frames_u8.contiguous()
+        n = frames_u8.numel() // (frames_u8.shape[-3] * frames_u8.shape[-2] * 3)
+        cols = ops.preprocess_patches(frames_u8, self.image, self.image, self.patch, mean, std, bgr)
+        return self._vision_from_cols(cols, n)
 
     @torch.no_grad()
     def text_hidden_pre_ln(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
