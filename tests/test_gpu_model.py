@@ -234,3 +234,21 @@ def test_video_clips_and_uint8_frames(cuda, clip_b32, sd_b32):
     ids[:, 0] = torch.tensor([5, 42], device=cuda)
     out = model(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=torch.from_numpy(frames).to(cuda))
     assert out["logits_per_image"].shape == (B, B) and torch.isfinite(out["loss"])
+
+
+def test_text_token0_shortcut_is_result_preserving(cuda, clip_b32):
+    """Track M pools the causal text tower at token 0, so running the tower on token 0 alone gives the same features
+    (SURVEY.md 8a-6 / 8d); the flag is opt-in and must not change any output."""
+    model = _make_model(cuda, clip_b32)
+    model.eval()
+    pix, ids, mask = O.synthetic_batch(6, seed=4)
+    ids[:, 0] = torch.arange(6) * 11 + 3
+    mask[2, 9:] = 0
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    with torch.no_grad():
+        dense = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+        model.text_token0_only = True
+        short = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    assert _rel(short["text_features"], dense["text_features"]) < 1e-5
+    assert abs(short["loss"].item() - dense["loss"].item()) < 1e-5
+    assert torch.equal(short["logits_per_image"].argmax(1), dense["logits_per_image"].argmax(1))

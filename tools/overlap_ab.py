@@ -30,7 +30,9 @@ def run(mode, n):
     t_cpu = time.perf_counter() - t0
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n, t_cpu / n * 1e3
-for r in range(3):
-    for mode in ("serial", "two_streams", "pipelined"):
+modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ("serial", "two_streams", "pipelined")
+rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+for r in range(rounds):
+    for mode in modes:
         g, c = run(mode, 60)
         print(f"round {r} {mode:12s} gpu {g:7.3f} ms/step   cpu enqueue {c:6.2f} ms/step", flush=True)

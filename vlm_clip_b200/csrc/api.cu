@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/vlmclip.h"
 #include "common.cuh"
@@ -27,6 +28,14 @@ int report_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("VLMCLIP_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 
 int sm_count() {
   static int n = []() {

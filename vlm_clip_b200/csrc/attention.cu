@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(256, 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                      const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_wait();
+  pdl_trigger();
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sV = sK + (size_t)Spad * KSTRIDE;
   uint8_t* sMask = reinterpret_cast<uint8_t*>(sV + (size_t)Spad * KSTRIDE);
@@ -236,9 +238,9 @@ int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, 
   }
   dim3 grid(B * H, groups);
   count_launch(1);
-  attention_fwd_kernel<<<grid, qw * 32, smem, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, key_mask, S, H,
-                                                       causal, scale * 1.4426950408889634f, Spad);
-  return report_cuda(cudaGetLastError(), "attention_fwd_kernel launch");
+  return report_cuda(launch_pdl(attention_fwd_kernel, grid, dim3(qw * 32), smem, stream, 1, (const __nv_bfloat16*)qkv,
+                                (__nv_bfloat16*)out, key_mask, S, H, causal, scale * 1.4426950408889634f, Spad),
+                     "attention_fwd_kernel launch");
 }
 
 }  // namespace vlmclip

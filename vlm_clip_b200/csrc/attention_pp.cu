@@ -176,6 +176,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   const int n_units = (p.num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // units of this CTA
   const int n_tiles = n_units * p.mtiles;
@@ -403,8 +405,7 @@ int launch_pp(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const PPParams& p
     VLMCLIP_CUDA(cudaFuncSetAttribute(attention_pp_kernel<GENERAL_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  attention_pp_kernel<GENERAL_MASK><<<grid, PP_THREADS, smem, s>>>(tmQ, tmKV, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(attention_pp_kernel<GENERAL_MASK>, dim3(grid), dim3(PP_THREADS), smem, s, 1, tmQ, tmKV, p);
   if (e != cudaSuccess) {
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, attention_pp_kernel<GENERAL_MASK>);

@@ -212,6 +212,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();     // prologue done; everything below touches global memory
+  pdl_trigger();  // the next kernel in the stream may start its own prologue as SMs free up
 
   // pair: tiles are 256 rows tall (m index counts pair tiles); this CTA's 128-row block is 2*m + rank
   const int num_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
@@ -599,25 +601,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   if (!PAIR) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
-    return report_cuda(cudaGetLastError(), "gemm_bf16_tn_kernel launch");
+    return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(grid), dim3(GEMM_THREADS),
+                                  L::DYN_BYTES, stream, 1, tmA, tmB, tmC, tmR, p),
+                       "gemm_bf16_tn_kernel launch");
   }
   // CTA pairs: cluster of 2 along x, one pair per two SMs
   const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = L::DYN_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return report_cuda(cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, tmA, tmB, tmC, tmR, p),
+  return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS),
+                                L::DYN_BYTES, stream, 2, tmA, tmB, tmC, tmR, p),
                      "gemm_bf16_tn_kernel<pair> launch");
 }
 

@@ -308,6 +308,8 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __re
 // (mean, M2) partials of 32-column blocks -> (mean, rstd) per row (Chan's parallel combination); 4 lanes per row
 __global__ void __launch_bounds__(256)
 ln_partials_to_stats_kernel(const float2* __restrict__ part, float2* __restrict__ stats, int M, int npart, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = blockIdx.x * 64 + (threadIdx.x >> 2);
   const int sub = threadIdx.x & 3;
   float msum = 0.f;
@@ -476,7 +478,7 @@ extern "C" int vlmclip_ln_partials_to_stats(const float* partials, float* stats_
                                             void* stream) {
   VLMCLIP_CHECK_ARG(partials && stats_out && M > 0 && npart > 0 && npart <= 64, "ln_partials_to_stats: bad arguments");
   count_launch(1);
-  ln_partials_to_stats_kernel<<<(M + 63) / 64, 256, 0, (cudaStream_t)stream>>>((const float2*)partials, (float2*)stats_out, M,
-                                                                              npart, eps);
-  return report_cuda(cudaGetLastError(), "ln_partials_to_stats_kernel launch");
+  return report_cuda(launch_pdl(ln_partials_to_stats_kernel, dim3((M + 63) / 64), dim3(256), 0, (cudaStream_t)stream, 1,
+                                (const float2*)partials, (float2*)stats_out, M, npart, eps),
+                     "ln_partials_to_stats_kernel launch");
 }

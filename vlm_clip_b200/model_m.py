@@ -99,6 +99,10 @@ class CLIPWithAdapters(nn.Module):
         # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
         self.overlap_towers = os.environ.get("VLMCLIP_OVERLAP_TOWERS", "1") != "0"
         self._tower_streams = None
+        # Opt-in, result-preserving shortcut: Track M pools the text tower at token 0 (model_m.py:102, the
+        # reference's BOS quirk) and the text tower is causal, so the pooled state depends on token 0 alone; with this
+        # flag the text tower runs on that one token per caption.  Off by default: the dense tower is the benchmark.
+        self.text_token0_only = False
         # on-GPU preprocessing of uint8 frames (extension): CLIP's normalisation by default, RGB channel order
         self.pixel_mean, self.pixel_std, self.frames_bgr = CLIP_MEAN, CLIP_STD, False
 
@@ -141,8 +145,15 @@ class CLIPWithAdapters(nn.Module):
             # raise through the adapter so the message names the missing kernel
             self.shared_adapters[0](None, None)
         bb = self._backbone()
+        input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
         hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
         return self._text_head(bb, hidden, input_ids.shape[0], input_ids.shape[1])
+
+    def _text_inputs(self, input_ids, attention_mask):
+        if self.text_token0_only and input_ids.shape[1] > 1:
+            input_ids = input_ids[:, :1].contiguous()
+            attention_mask = None if attention_mask is None else attention_mask[:, :1].contiguous()
+        return input_ids, attention_mask
 
     def _text_head(self, bb, hidden, B, S):
         # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32
@@ -248,6 +259,7 @@ class CLIPWithAdapters(nn.Module):
                 st.wait_event(inputs_ready)
             else:
                 st.wait_stream(main)
+        input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
         with torch.cuda.stream(txt):
             t_hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)
         with torch.cuda.stream(vis):
