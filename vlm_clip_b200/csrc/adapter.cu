@@ -23,7 +23,7 @@ void count_launch(int n);
 namespace {
 
 constexpr int RB = 4;  // rows per CTA
-constexpr int NT = 256;
+constexpr int NT = 1024;
 
 struct AdapterArgs {
   const void* x;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NT) adapter_bwd_rows_kernel(const AdapterArgs 
 }
 
 // Weight gradients: blockIdx.z = 0: dW2[d][j] = sum_r du[r][d] h[r][j];  1: dW1[j][d] = sum_r dp[r][j] x[r][d]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TF_THREADS)
 adapter_wgrad_kernel(const float* __restrict__ du, const float* __restrict__ h, const float* __restrict__ dp,
                      const float* __restrict__ x, float* __restrict__ dW1, float* __restrict__ dW2, int R, int D,
                      int A) {
@@ -412,7 +412,7 @@ adapter_colsum_kernel(const float* __restrict__ du, const float* __restrict__ dy
 }
 
 // y[R,N] = x[R,K] W[N,K]^T (+ b)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TF_THREADS)
 linear_f32_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ W, const float* __restrict__ b,
                   float* __restrict__ y, int R, int N, int K) {
   const int m0 = blockIdx.x * TF_TILE, n0 = blockIdx.y * TF_TILE;
@@ -424,7 +424,7 @@ linear_f32_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
       });
 }
 // dx[R,K] = dy[R,N] W[N,K]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TF_THREADS)
 linear_f32_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int R,
                         int N, int K) {
   const int m0 = blockIdx.x * TF_TILE, n0 = blockIdx.y * TF_TILE;  // n over K (input features)
@@ -545,7 +545,7 @@ extern "C" int vlmclip_adapter_bwd(const void* x, int x_bf16, int64_t ldx, const
   adapter_bwd_rows_kernel<<<(R + RB - 1) / RB, NT, smem, s>>>(a);
   VLMCLIP_CUDA(cudaGetLastError());
   dim3 grid((D + TF_TILE - 1) / TF_TILE, (A + TF_TILE - 1) / TF_TILE, 2);
-  adapter_wgrad_kernel<<<grid, 256, 0, s>>>(a.ws_du, a.ws_h, a.ws_dp, a.ws_x, dW1, dW2, R, D, A);
+  adapter_wgrad_kernel<<<grid, TF_THREADS, 0, s>>>(a.ws_du, a.ws_h, a.ws_dp, a.ws_x, dW1, dW2, R, D, A);
   VLMCLIP_CUDA(cudaGetLastError());
   const bool ln = post == VLMCLIP_ADAPTER_RESIDUAL_LN;
   adapter_colsum_kernel<<<(D + A + 31) / 32, 256, 0, s>>>(a.ws_du, dy, a.ws_zhat, a.ws_dp, db1, db2,
@@ -558,7 +558,7 @@ extern "C" int vlmclip_linear_f32(const float* x, int64_t ldx, const float* W, c
   VLMCLIP_CHECK_ARG(x && W && y && R > 0 && N > 0 && K > 0 && ldx >= K, "linear_f32: bad arguments");
   dim3 grid((R + TF_TILE - 1) / TF_TILE, (N + TF_TILE - 1) / TF_TILE);
   count_launch(1);
-  linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, W, b, y, R, N, K);
+  linear_f32_kernel<<<grid, TF_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, W, b, y, R, N, K);
   return report_cuda(cudaGetLastError(), "linear_f32_kernel launch");
 }
 
@@ -567,6 +567,6 @@ extern "C" int vlmclip_linear_f32_dgrad(const float* dy, const float* W, float* 
   VLMCLIP_CHECK_ARG(dy && W && dx && R > 0 && N > 0 && K > 0, "linear_f32_dgrad: bad arguments");
   dim3 grid((R + TF_TILE - 1) / TF_TILE, (K + TF_TILE - 1) / TF_TILE);
   count_launch(1);
-  linear_f32_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, W, dx, R, N, K);
+  linear_f32_dgrad_kernel<<<grid, TF_THREADS, 0, (cudaStream_t)stream>>>(dy, W, dx, R, N, K);
   return report_cuda(cudaGetLastError(), "linear_f32_dgrad_kernel launch");
 }

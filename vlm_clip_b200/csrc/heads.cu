@@ -65,7 +65,7 @@ l2norm_rows_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy
 
 // ---------------------------------------------------------------- similarity logits
 // Z[i][j] = s * sum_p tn[i][p] * in[j][p]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TF_THREADS)
 sim_logits_kernel(const float* __restrict__ tn, const float* __restrict__ in_, float* __restrict__ Z, float s, int N,
                   int P) {
   const int m0 = blockIdx.x * TF_TILE, n0 = blockIdx.y * TF_TILE;
@@ -152,7 +152,7 @@ __device__ __forceinline__ float clip_G(const float* Z, const float* lse_r, cons
 
 // blockIdx.z = 0: dtn[i][p] = s * sum_j G[i][j] in[j][p]   (i in local rows)
 // blockIdx.z = 1: din[j][p] = s * sum_i G[i][j] tn[i][p]   (j in local rows)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TF_THREADS)
 clip_grad_kernel(const float* __restrict__ Z, const float* __restrict__ lse_r, const float* __restrict__ lse_c,
                  const float* __restrict__ tn, const float* __restrict__ in_, float* __restrict__ dtn,
                  float* __restrict__ din, float s, int N, int P, int row0, int nloc) {
@@ -377,7 +377,7 @@ extern "C" int vlmclip_clip_loss(const float* txt, const float* img, float logit
   l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(txt, nullptr, txt_n, inv_t, nullptr, N, P);
   l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, s>>>(img, nullptr, img_n, inv_i, nullptr, N, P);
   VLMCLIP_CUDA(cudaGetLastError());
-  sim_logits_kernel<<<dim3(tiles_n, tiles_n), 256, 0, s>>>(txt_n, img_n, Z, logit_scale_exp, N, P);
+  sim_logits_kernel<<<dim3(tiles_n, tiles_n), TF_THREADS, 0, s>>>(txt_n, img_n, Z, logit_scale_exp, N, P);
   row_lse_kernel<<<(N + 7) / 8, 256, 0, s>>>(Z, lse_r, N);
   col_lse_kernel<<<(N + 31) / 32, 256, 0, s>>>(Z, lse_c, N);
   clip_loss_reduce_kernel<<<1, 256, 0, s>>>(Z, lse_r, lse_c, loss, N);
@@ -385,7 +385,7 @@ extern "C" int vlmclip_clip_loss(const float* txt, const float* img, float logit
   if (d_txt != nullptr && nloc > 0) {
     count_launch(2);
     dim3 g((nloc + TF_TILE - 1) / TF_TILE, (P + TF_TILE - 1) / TF_TILE, 2);
-    clip_grad_kernel<<<g, 256, 0, s>>>(Z, lse_r, lse_c, txt_n, img_n, dtn, din, logit_scale_exp, N, P, row0, nloc);
+    clip_grad_kernel<<<g, TF_THREADS, 0, s>>>(Z, lse_r, lse_c, txt_n, img_n, dtn, din, logit_scale_exp, N, P, row0, nloc);
     clip_norm_bwd_kernel<<<dim3((nloc + 7) / 8, 2), 256, 0, s>>>(txt_n, img_n, inv_t, inv_i, dtn, din, d_txt, d_img,
                                                                 P, row0, nloc);
     VLMCLIP_CUDA(cudaGetLastError());
