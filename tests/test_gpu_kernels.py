@@ -437,6 +437,31 @@ def test_fused_adamw_matches_torch(cuda):
             assert torch.allclose(p, q, atol=1e-7, rtol=1e-5)
 
 
+@pytest.mark.parametrize("S,late", [(197, 128), (197, 40), (160, 96)])
+def test_attention_late_maximum_rescale(cuda, S, late):
+    """The tcgen05 softmax takes its reference exponent from the first 32 keys; keys >= `late` carry logits ~100 octaves
+    above everything before them, which forces the exact power-of-two rescale of the P already written."""
+    from vlm_clip_b200 import ops
+
+    B, H = 2, 3
+    D = H * 64
+    g = _gen(S + late)
+    q = torch.randn(B, S, H, 64, device=cuda, generator=g) * 0.3
+    k = torch.randn(B, S, H, 64, device=cuda, generator=g) * 0.3
+    v = torch.randn(B, S, H, 64, device=cuda, generator=g)
+    u = torch.randn(H, 64, device=cuda, generator=g)
+    u = u / u.norm(dim=1, keepdim=True) * 8.0
+    q = q + 3.0 * u                       # every query shares a large component ...
+    k[:, late:] = k[:, late:] + 3.0 * u   # ... that only the late keys match: logits jump by ~9*64/8 = 72 nats
+    k[0, 60:64] += 1.5 * u                # a smaller bump in an earlier chunk (second rescale for batch 0)
+    qkv = torch.stack([q, k, v], 2).reshape(B * S, 3 * D).to(bf16)
+    out = ops.attention(qkv, B, S, H)
+    qf, kf, vf = qkv.float().view(B, S, 3, D).unbind(2)
+    ref = O.attention_core(qf, kf, vf, H, False, None).reshape(B * S, D)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 8e-3, f"rel err {_rel(out, ref)}"
+
+
 @pytest.mark.parametrize("hs,ws,h,patch,bgr", [(60, 80, 32, 16, False), (32, 32, 32, 16, True), (45, 61, 28, 14, False)])
 def test_preprocess_patches_bit_exact(cuda, hs, ws, h, patch, bgr):
     """uint8 frames -> resize -> /255 -> normalise -> bf16 im2col: integer resize + IEEE float ops, so bit exact against

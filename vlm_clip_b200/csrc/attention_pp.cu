@@ -6,14 +6,15 @@
 // t & 1 and to TMEM S/P buffer t & 1, so one warpgroup's softmax overlaps the other one's MMAs; O is drained and
 // written out by a third warpgroup, off the softmax path.  Measured limits on B200 (tools/mufu_bench.cu and the
 // VLMCLIP_ATTN_DEBUG=1 phase timers): MUFU.EX2 issues one warp instruction per 8 clk per scheduler, tcgen05.ld
-// delivers about 64 B/clk/SM, so the two passes over S (it does not fit the register file at one thread per row) and
-// the exp2 pass are the phases that bound the kernel.
+// delivers about 64 B/clk/SM, so S is streamed from TMEM exactly once (a 208-score row does not fit one thread's
+// registers) with the exp2 work hidden behind nothing but the other warpgroup's tile.
 //   warp 0     TMA: per unit Q [128*mtiles x 64], K [Npad x 64], V [Npad x 64] (rows of the fused qkv activation, SW128)
 //   warp 1     tcgen05: S = Q K^T (SS MMA, M=128, N=Npad, 4 k-steps) -> TMEM buffer t&1, issued right behind P.V(t-2);
 //              O = P V (TS MMA: A = P from TMEM, B = V as an MN-major smem operand) -> TMEM columns [448, 512)
-//   warps 4-11 softmax, ONE thread per query row, no cross-thread exchange: pass 1 reads the row from TMEM for its
-//              maximum, pass 2 reads it again, p = exp2(s*c - m*c) truncated to bf16 with integer ops (F2FP shares the
-//              SFU pipe with MUFU.EX2), row sum over the truncated values, P written over the S columns (tcgen05.st)
+//   warps 4-11 softmax, ONE thread per query row, no cross-thread exchange, ONE pass over S: the reference exponent is the
+//              maximum of the row's first chunk (raised by whole octaves, exactly, if a later chunk ever exceeds it by
+//              2^16), p = exp2(s*c - ref) truncated to bf16 with integer ops (F2FP shares the SFU pipe with MUFU.EX2),
+//              row sum over the truncated values, P written over the S columns (tcgen05.st)
 //   warps 12-15 epilogue: tcgen05.ld O (frees O for the next P.V), * 1/rowsum, bf16, through a swizzled smem tile so
 //              that global stores are row-contiguous
 #include <cstdio>
@@ -128,6 +129,45 @@ __device__ __forceinline__ void exp_chunk(const PPParams& p, const uint32_t (&cu
     }
   }
   tmem_st_32x32b_x16(taddr, pk);
+}
+
+// One 32-column chunk of the single-pass softmax: chunk maximum -> (rarely) raise the reference by whole octaves and
+// rescale what was already produced -> exp2 / truncate / sum / pack / store.
+template <bool GENERAL_MASK>
+__device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t (&cur)[32], int ch, int kmax_warp,
+                                              const uint8_t* km, int qrow, float c, float& off, bool& has_ref,
+                                              float (&l4)[4], uint32_t tb) {
+  const int k0 = ch * 32;
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  max_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, m4);
+  const float mcs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * c;  // -inf: no visible key in this chunk
+  if (!has_ref && mcs > -INFINITY) {
+    off = mcs;
+    has_ref = true;
+  }
+  const float excess = has_ref ? mcs - off : 0.f;
+  const bool need = excess > 16.f;
+  if (__any_sync(0xffffffffu, need)) {  // warp-uniform: the TMEM accesses below are warp collectives
+    const float d = need ? ceilf(excess) : 0.f;
+    const float f = exp2f(-d);  // exact power of two
+    tmem_wait_st();
+    for (int j = 0; j < ch; ++j) {
+      uint32_t pk[16];
+      tmem_ld_32x32b_x16(tb + j * 16, pk);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t lo = __float_as_uint(__uint_as_float(pk[i] << 16) * f) & 0xffff0000u;
+        const uint32_t hi = __float_as_uint(__uint_as_float(pk[i] & 0xffff0000u) * f) & 0xffff0000u;
+        pk[i] = __byte_perm(lo, hi, 0x7632);
+      }
+      tmem_st_32x32b_x16(tb + j * 16, pk);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l4[i] *= f;
+    off += d;
+  }
+  exp_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, c, off, l4, tb + ch * 16);
 }
 
 template <bool GENERAL_MASK>
@@ -316,7 +356,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tb = tmem_base + lane_off + wg * p.nb;
 
     long long tk[5] = {0, 0, 0, 0, 0};
-    const bool dbg = p.debug == 1 && blockIdx.x == 0 && wq == 0 && lane == 0;
+    long long tw[2] = {0, 0};
+    const bool dbgw = p.debug == 1 && blockIdx.x == 0 && wq == 0;
+    const bool dbg = dbgw && lane == 0;
     int ntl = 0;
     for (int t = wg; t < n_tiles; t += 2, ++ntl) {
       long long t0 = dbg ? clock64() : 0;
@@ -333,45 +375,34 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tcgen05_fence_after();
       if (dbg) { long long x = clock64(); tk[0] += x - t0; t0 = x; }
       float l = 0.f;
-      float off = 0.f;
       if (warp_valid) {
         __syncwarp();
-        // ---- pass 1: row maximum.  tcgen05.wait::ld covers every outstanding load, so the row is streamed through two
-        // register buffers: chunk i+1 is in flight while chunk i is reduced ----
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        {
-          uint32_t a0[32], b0[32];
-          tmem_ld_32x32b_x32(tb, a0);
-          for (int ch = 0; ch < nch; ch += 2) {
-            tmem_wait_ld();
-            if (ch + 1 < nch) tmem_ld_32x32b_x32(tb + (ch + 1) * 32, b0);
-            max_chunk<GENERAL_MASK>(p, a0, ch * 32, kmax_warp, km, qrow, m4);
-            if (ch + 1 < nch) {
-              tmem_wait_ld();
-              if (ch + 2 < nch) tmem_ld_32x32b_x32(tb + (ch + 2) * 32, a0);
-              max_chunk<GENERAL_MASK>(p, b0, ch * 32 + 32, kmax_warp, km, qrow, m4);
-            }
-          }
-        }
-        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        off = (m == -INFINITY ? 0.f : m) * c;
-      }
-      if (dbg) { long long x = clock64(); tk[1] += x - t0; t0 = x; }
-      if (warp_valid) {
-        // ---- pass 2: p = exp2(s*c - m*c) -> bf16 by truncation, row sum over the truncated values, P over S ----
+        // ---- single pass over S (TMEM reads are the scarce resource: ~64 B/clk/SM): softmax is shift invariant, so the
+        // reference `off` only has to keep exp2 in range.  It starts as the maximum of the row's first visible chunk and
+        // is raised by an INTEGER number of octaves (exact rescale of the P already written and of the row sum) only
+        // when a later chunk exceeds it by more than 16 octaves: never for trained CLIP weights, still exact if it does.
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        {
-          uint32_t sa[32], sb[32];
-          tmem_ld_32x32b_x32(tb, sa);
-          for (int ch = 0; ch < nch; ch += 2) {
+        float off = 0.f;
+        bool has_ref = false;
+        uint32_t sa[32], sb[32];
+        tmem_ld_32x32b_x32(tb, sa);
+        for (int ch = 0; ch < nch; ch += 2) {
+          long long w0 = dbgw ? clock64() : 0;
+          tmem_wait_ld();
+          if (ch + 1 < nch) tmem_ld_32x32b_x32(tb + (ch + 1) * 32, sb);
+          long long w1 = dbgw ? clock64() : 0;
+          softmax_chunk<GENERAL_MASK>(p, sa, ch, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
+          long long w2 = dbgw ? clock64() : 0;
+          tw[0] += w1 - w0;
+          tw[1] += w2 - w1;
+          if (ch + 1 < nch) {
             tmem_wait_ld();
-            if (ch + 1 < nch) tmem_ld_32x32b_x32(tb + (ch + 1) * 32, sb);
-            exp_chunk<GENERAL_MASK>(p, sa, ch * 32, kmax_warp, km, qrow, c, off, l4, tb + ch * 16);
-            if (ch + 1 < nch) {
-              tmem_wait_ld();
-              if (ch + 2 < nch) tmem_ld_32x32b_x32(tb + (ch + 2) * 32, sa);
-              exp_chunk<GENERAL_MASK>(p, sb, ch * 32 + 32, kmax_warp, km, qrow, c, off, l4, tb + ch * 16 + 16);
-            }
+            if (ch + 2 < nch) tmem_ld_32x32b_x32(tb + (ch + 2) * 32, sa);
+            long long w3 = dbgw ? clock64() : 0;
+            softmax_chunk<GENERAL_MASK>(p, sb, ch + 1, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
+            long long w4 = dbgw ? clock64() : 0;
+            tw[0] += w3 - w2;
+            tw[1] += w4 - w3;
           }
         }
         l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -385,8 +416,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (dbg) { long long x = clock64(); tk[4] += x - t0; t0 = x; }
     }
     if (dbg && ntl > 0)
-      printf("attn-pp dbg wg %d tiles %d cycles/tile: wait_s %lld max %lld exp+st %lld publish %lld\n", wg, ntl,
-             tk[0] / ntl, tk[1] / ntl, tk[3] / ntl, tk[4] / ntl);
+      printf("attn-pp dbg wg %d tiles %d cycles/tile: wait_s %lld softmax %lld (wait+ld %lld, chunks %lld) publish %lld\n", wg, ntl,
+             tk[0] / ntl, tk[3] / ntl, tw[0] / ntl, tw[1] / ntl, tk[4] / ntl);
   }
 
   tcgen05_fence_before();
