@@ -252,3 +252,43 @@ def test_text_token0_shortcut_is_result_preserving(cuda, clip_b32):
     assert _rel(short["text_features"], dense["text_features"]) < 1e-5
     assert abs(short["loss"].item() - dense["loss"].item()) < 1e-5
     assert torch.equal(short["logits_per_image"].argmax(1), dense["logits_per_image"].argmax(1))
+
+
+def test_config3_vit_l14_dims_with_peclip_adapters(cuda):
+    """BASELINE config 3 at reduced depth / batch: ViT-L/14 dimensions (S = 257, D = 1024 / 768, patch 14, 16 / 12 heads)
+    with PE-CLIP TextualAdapters in the adapter slots, against the fp32 oracle; gradients flow to the adapters only."""
+    L14 = "openai/clip-vit-large-patch14"
+    clip = O.build_hf_clip(L14, seed=0, vision_layers=2, text_layers=2).to(cuda)
+    for p_ in clip.parameters():
+        p_.requires_grad_(False)
+    sd = {k: v.detach() for k, v in clip.state_dict().items()}
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+
+    torch.manual_seed(3)
+    model = CLIPWithAdapters(clip=clip, use_shared_adapters=False, adapter_kind="peclip").to(cuda)
+    model.train()
+    Bn = 4
+    pix, ids, mask = O.synthetic_batch(Bn, seed=6)
+    ids[:, 0] = torch.arange(Bn) * 101 + 7
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    out = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    out["loss"].backward()
+    ta = {k: v.detach().clone().requires_grad_(True) for k, v in model.text_adapter.state_dict().items()}
+    va = {k: v.detach().clone().requires_grad_(True) for k, v in model.vision_adapter.state_dict().items()}
+    t_hid = O.text_tower(sd, ids, mask, 12)
+    v_hid = O.vision_tower(sd, pix, 16)
+    t_feat = O.peclip_textual_adapter(t_hid, ta)[:, 0] @ sd["text_projection.weight"].t()
+    i_feat = O.peclip_textual_adapter(v_hid, va)[:, 0] @ sd["visual_projection.weight"].t()
+    ref = O.contrastive_loss(t_feat, i_feat, sd["logit_scale"])
+    ref["loss"].backward()
+    assert out["image_features"].shape == (Bn, 768)
+    assert _rel(out["image_features"], ref["image_features"]) < FEAT_TOL
+    assert _rel(out["text_features"], ref["text_features"]) < FEAT_TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) < LOSS_TOL
+    assert torch.equal(out["logits_per_image"].argmax(1), ref["logits_per_image"].argmax(1))
+    for mod, refd in ((model.text_adapter, ta), (model.vision_adapter, va)):
+        for k, p_ in mod.named_parameters():
+            assert "adapter" not in k and p_.grad is not None  # names carry "adapter" through the attribute prefix
+            cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), refd[k].grad.flatten(), dim=0).item()
+            assert cos > 0.98, (k, cos)
+    assert all("adapter" in n for n, p_ in model.named_parameters() if p_.requires_grad)

@@ -29,6 +29,7 @@ import torch.nn as nn
 from . import _native as N
 from . import ops
 from .adapter.clip_adapter import SharedMHSAttentionAdapter, TextAdapter, VisionAdapter
+from .adapter.peclip import TextualAdapter
 from .constants import CLIP_MEAN, CLIP_STD
 from .towers import NativeClipTowers
 
@@ -65,6 +66,7 @@ class CLIPWithAdapters(nn.Module):
         *,
         clip=None,
         processor=None,
+        adapter_kind="clip_adapter",
     ):
         super().__init__()
         # `clip=` / `processor=` are extensions: a ready CLIPModel (e.g. random-init on an offline box)
@@ -81,10 +83,17 @@ class CLIPWithAdapters(nn.Module):
         self.text_adapter = None
         self.vision_adapter = None
         self.shared_adapters = None
+        # `adapter_kind` is an extension (BASELINE config 3): "peclip" puts adapter/peclip.py's TextualAdapter
+        # (up(gelu(down x)) + x, no LayerNorm) into the same two slots; the reference wires PE-CLIP adapters into no model.
+        if adapter_kind not in ("clip_adapter", "peclip"):
+            raise ValueError(f"adapter_kind must be 'clip_adapter' or 'peclip', got {adapter_kind!r}")
+        self.adapter_kind = adapter_kind
         if self.use_text_adapter:
-            self.text_adapter = TextAdapter(text_hidden_size, text_adapter_size)
+            self.text_adapter = (TextAdapter(text_hidden_size, text_adapter_size) if adapter_kind == "clip_adapter"
+                                 else TextualAdapter(text_hidden_size, text_adapter_size))
         if self.use_vision_adapter:
-            self.vision_adapter = VisionAdapter(vision_hidden_size, vision_adapter_size)
+            self.vision_adapter = (VisionAdapter(vision_hidden_size, vision_adapter_size) if adapter_kind == "clip_adapter"
+                                   else TextualAdapter(vision_hidden_size, vision_adapter_size))
         if self.use_shared_adapters:
             self.shared_adapters = nn.ModuleList(
                 [SharedMHSAttentionAdapter(text_hidden_size, vision_hidden_size) for _ in range(shared_adapter_layers)])
