@@ -125,6 +125,15 @@ int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const 
 int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                           float scale, void* stream);
 
+/* Single-query attention, head_dim 64: out[b] = softmax(q[b] K^T * scale) V per head, ONE query row per batch element.
+ * Replaces nn.MultiheadAttention's core in SharedMHSAttentionAdapter (adapter/clip_adapter.py:114, as called from
+ * model_m.py:93-100 with the vision position table as keys/values and only token 0 consumed, model_m.py:102), and
+ * serves the CLS-only evaluation of the last vision layer.  q: bf16, row b at q + b*q_stride (elements), heads
+ * contiguous 64-wide; k, v: bf16, key j of batch b at k + b*kv_batch_stride + j*kv_row_stride (kv_batch_stride = 0:
+ * keys/values shared by the batch); out: bf16 [B, H*64].  S <= 512. */
+int vlmclip_attention_1q(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
+                         int64_t kv_batch_stride, void* out, int B, int S, int H, float scale, void* stream);
+
 /* One frozen tower, all layers, in one call: the launch sequence of towers.NativeClipTowers._encoder (the reference's
  * CLIPEncoder loop, HF modeling_clip.py:355-386 x num_hidden_layers) issued natively.  Same kernels as the per-op
  * entry points above; this exists because issuing ~170 ops per step from the interpreter cost more host time than the

@@ -258,6 +258,31 @@ def mhsa_adapter(x: Tensor, a: Dict[str, Tensor], heads: int) -> Tensor:
     return layer_norm(y + x, a["layer_norm.weight"], a["layer_norm.bias"])
 
 
+def shared_mhs_adapter(t: Tensor, table: Tensor, a: Dict[str, Tensor], heads: int = 8) -> Tensor:
+    """SharedMHSAttentionAdapter.forward in eval mode (adapter/clip_adapter.py:99-128): t [B, T, 512] text states,
+    table [1 or B, S, 768] image-side states (model_m.py:93-96 passes the vision position table, batch 1)."""
+    h = linear(t, a["text_proj.weight"], a["text_proj.bias"])
+    e = linear(table, a["image_proj.weight"], a["image_proj.bias"])
+    kv = layer_norm(e, a["norm1.weight"], a["norm1.bias"])
+    h = layer_norm(h, a["norm2.weight"], a["norm2.bias"])
+    D = h.shape[-1]
+    wq, wk, wv = a["cross_attn.in_proj_weight"].split(D, dim=0)
+    bq, bk, bv = a["cross_attn.in_proj_bias"].split(D, dim=0)
+    q, k, v = linear(h, wq, bq), linear(kv, wk, bk), linear(kv, wv, bv)
+    B, T, _ = q.shape
+    k, v = k.expand(B, -1, -1), v.expand(B, -1, -1)
+    hd = D // heads
+    qh = q.view(B, T, heads, hd).transpose(1, 2)
+    kh = k.reshape(B, -1, heads, hd).transpose(1, 2)
+    vh = v.reshape(B, -1, heads, hd).transpose(1, 2)
+    p = torch.softmax((qh @ kh.transpose(-1, -2)) * hd ** -0.5, dim=-1)
+    att = (p @ vh).transpose(1, 2).reshape(B, T, D)
+    h = h + linear(att, a["cross_attn.out_proj.weight"], a["cross_attn.out_proj.bias"])
+    z = layer_norm(h, a["norm3.weight"], a["norm3.bias"])
+    z = linear(F.gelu(linear(z, a["mlp.0.weight"], a["mlp.0.bias"])), a["mlp.2.weight"], a["mlp.2.bias"])
+    return h + z
+
+
 def model_m_forward(sd, heads_t, heads_v, input_ids, attention_mask, pixel_values, text_adapter, vision_adapter):
     t = model_m_text_features(sd, heads_t, input_ids, attention_mask, text_adapter)
     i = model_m_image_features(sd, heads_v, pixel_values, vision_adapter)

@@ -113,6 +113,24 @@ def golden_adapters():
     return out
 
 
+def golden_shared_adapter():
+    """SharedMHSAttentionAdapter (adapter/clip_adapter.py:69-128) in eval mode (dropout off), called the way
+    model_m.py:93-100 calls it: a batch of text states against ONE [1, S_v, 768] table.  The reference passes the
+    batch-1 table straight to nn.MultiheadAttention, which only works at text batch 1, so the golden
+    run loops over the captions; weights are reproducible from the seed (same construction order as the mirror)."""
+    from adapter.clip_adapter import SharedMHSAttentionAdapter
+
+    torch.manual_seed(11)
+    mod = SharedMHSAttentionAdapter().eval()
+    g = torch.Generator().manual_seed(12)
+    xt = torch.randn(3, 77, 512, generator=g)
+    table = torch.randn(1, 50, 768, generator=g) * 0.5
+    with torch.no_grad():
+        y = torch.cat([mod(xt[i:i + 1], table) for i in range(xt.shape[0])], 0)
+    return {"seed_module": 11, "seed_inputs": 12, "w_head": mod.text_proj.weight.reshape(-1)[:16].clone(),
+            "y_tok01": y[:, :2, :].clone(), "y_abs_sum": y.double().abs().sum().item()}
+
+
 def golden_track_m():
     """G1: CLIPWithAdapters (ViT-B/32 dims, seeded random init), B=8, .train(): loss/logits/features/adapter grads,
     then two steps of the reference CLIPAdapterTrainer loop (trainer.py:73-99)."""
@@ -237,6 +255,7 @@ def main():
     torch.save(golden_adapters(), OUT / "adapters.pt")
     torch.save(golden_track_m(), OUT / "track_m.pt")
     torch.save(golden_track_tv(), OUT / "track_tv.pt")
+    torch.save(golden_shared_adapter(), OUT / "shared_adapter.pt")
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size)
 

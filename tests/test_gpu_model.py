@@ -292,3 +292,40 @@ def test_config3_vit_l14_dims_with_peclip_adapters(cuda):
             cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), refd[k].grad.flatten(), dim=0).item()
             assert cos > 0.98, (k, cos)
     assert all("adapter" in n for n, p_ in model.named_parameters() if p_.requires_grad)
+
+
+def test_shared_mhs_adapter_inference(cuda, clip_b32):
+    """Row 8a-8: the cross-modal adapter's inference path on the GPU against the fp32 oracle, stand-alone and inside
+    CLIPWithAdapters (token-0 evaluation, model_m.py:93-102); training it raises."""
+    from vlm_clip_b200 import _native as N
+    from vlm_clip_b200.adapter.clip_adapter import SharedMHSAttentionAdapter
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+
+    torch.manual_seed(11)
+    mod = SharedMHSAttentionAdapter().to(cuda).eval()
+    g = torch.Generator().manual_seed(12)
+    xt = torch.randn(3, 77, 512, generator=g).to(cuda)
+    table = (torch.randn(1, 50, 768, generator=g) * 0.5).to(cuda)
+    a = {k: v.detach() for k, v in mod.state_dict().items()}
+    with torch.no_grad():
+        y = mod(xt, table)
+    ref = O.shared_mhs_adapter(xt, table, a)
+    assert y.shape == ref.shape and _rel(y, ref) < 1e-2, _rel(y, ref)
+    mod.train()
+    with pytest.raises(N.NativeError):
+        mod(xt, table)
+
+    torch.manual_seed(2)
+    model = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=True, shared_adapter_layers=2).to(cuda).eval()
+    pix, ids, mask = O.synthetic_batch(4, seed=8)
+    ids[:, 0] = torch.arange(4) * 13 + 2
+    with torch.no_grad():
+        t = model.get_text_features(ids.to(cuda), mask.to(cuda))
+    sd = {k: v.detach() for k, v in clip_b32.state_dict().items()}
+    hid = O.seq_adapter(O.text_tower(sd, ids.to(cuda), mask.to(cuda), 8),
+                        {k: v.detach() for k, v in model.text_adapter.state_dict().items()})
+    tab = sd["vision_model.embeddings.position_embedding.weight"].unsqueeze(0)
+    for ad in model.shared_adapters:
+        hid = O.shared_mhs_adapter(hid, tab, {k: v.detach() for k, v in ad.state_dict().items()})
+    ref_t = hid[:, 0] @ sd["text_projection.weight"].t()
+    assert _rel(t, ref_t) < FEAT_TOL, _rel(t, ref_t)

@@ -248,3 +248,21 @@ def test_adamw_clip_reference_matches_torch():
     assert abs(norm.item() - n2.item()) < 1e-5
     for (p, _, _), q in zip(out, qs):
         assert torch.allclose(p, q.detach(), atol=1e-7)
+
+
+def test_shared_mhs_adapter_matches_executed_reference():
+    """SharedMHSAttentionAdapter (adapter/clip_adapter.py:69-128), eval mode: oracle restatement vs the reference module's
+    own output (tests/golden/shared_adapter.pt, written by oracle/make_golden.py)."""
+    from vlm_clip_b200.adapter.clip_adapter import SharedMHSAttentionAdapter
+
+    gold = torch.load(GOLD / "shared_adapter.pt")
+    torch.manual_seed(gold["seed_module"])
+    mod = SharedMHSAttentionAdapter()  # same construction order as the reference -> same default-init weights
+    assert torch.equal(mod.text_proj.weight.reshape(-1)[:16], gold["w_head"])
+    g = torch.Generator().manual_seed(gold["seed_inputs"])
+    xt = torch.randn(3, 77, 512, generator=g)
+    table = torch.randn(1, 50, 768, generator=g) * 0.5
+    a = {k: v.detach() for k, v in mod.state_dict().items()}
+    y = O.shared_mhs_adapter(xt, table, a)
+    assert torch.allclose(y[:, :2, :], gold["y_tok01"], atol=2e-5, rtol=1e-5)
+    assert abs(y.double().abs().sum().item() - gold["y_abs_sum"]) / gold["y_abs_sum"] < 1e-6

@@ -66,8 +66,8 @@ class SharedMHSAttentionAdapter(nn.Module):
 
     Parameter layout and state-dict keys match the reference (text_proj, image_proj, cross_attn, norm1..3, mlp).
     The reference can only execute this module at batch size 1 (model_m.py:96-100 passes a batch-1 K/V to
-    nn.MultiheadAttention) and it hard-codes 512/768 widths; it is outside the accelerated hot
-    path.  forward() therefore raises instead of silently running a non-native path.
+    nn.MultiheadAttention) and it hard-codes 512/768 widths.  forward() runs the inference path
+    natively; training it raises instead of silently running a non-native path.
     """
 
     def __init__(self, text_input_size=512, image_input_size=768, hidden_size=512, num_heads=8, dropout=0.1):
@@ -81,9 +81,57 @@ class SharedMHSAttentionAdapter(nn.Module):
         self.norm3 = nn.LayerNorm(hidden_size)
         self.mlp = nn.Sequential(nn.Linear(hidden_size, hidden_size * 4), nn.GELU(),
                                  nn.Linear(hidden_size * 4, hidden_size), nn.Dropout(dropout))
+        self._packed = None
+
+    def _pack(self, dev):
+        ps = [self.text_proj.weight, self.image_proj.weight, self.cross_attn.in_proj_weight, self.cross_attn.out_proj.weight,
+              self.mlp[0].weight, self.mlp[2].weight]
+        key = (tuple(p._version for p in ps), str(dev))
+        if self._packed is None or self._packed[0] != key:
+            D = self.text_proj.out_features
+            b = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+            w_in = self.cross_attn.in_proj_weight
+            self._packed = (key, {"tp": b(self.text_proj.weight), "ip": b(self.image_proj.weight), "wq": b(w_in[:D]),
+                                  "wkv": b(w_in[D:]), "wo": b(self.cross_attn.out_proj.weight), "w1": b(self.mlp[0].weight),
+                                  "w2": b(self.mlp[2].weight)})
+        return self._packed[1]
 
     def forward(self, hidden_states, encoder_hidden_states):
-        raise N.NativeError(
-            "SharedMHSAttentionAdapter has no sm_100a kernel yet (cross-attention with unequal sequence lengths); "
-            "construct CLIPWithAdapters(use_shared_adapters=False) — the configuration the reference itself can "
-            "train (trainer.py:191-195).")
+        """Inference path (eval mode / no_grad) on the tensor cores: GEMM -> LayerNorm -> single-query attention per text
+        row against the projected table -> GEMM (+residual) -> LayerNorm -> MLP (+residual).
+
+        hidden_states [B, T, text_input_size]; encoder_hidden_states [1, S, image_input_size] (what model_m.py:93-96
+        passes: the vision position table, one for the whole batch).  Every text row attends to the table on its own,
+        so the reference's batch-1 limitation does not apply here.  Training this module (dropout, backward through
+        the attention and the table path) has no kernel yet and raises."""
+        if self.training or (torch.is_grad_enabled() and (hidden_states.requires_grad or
+                                                          any(p.requires_grad for p in self.parameters()))):
+            raise N.NativeError(
+                "SharedMHSAttentionAdapter: only the inference path (eval mode under torch.no_grad()) has sm_100a kernels; "
+                "train with CLIPWithAdapters(use_shared_adapters=False) — the configuration the reference itself can train "
+                "(trainer.py:191-195)")
+        if encoder_hidden_states.dim() != 3 or encoder_hidden_states.shape[0] != 1:
+            raise ValueError("encoder_hidden_states must be [1, S, image_input_size] (one table shared by the batch)")
+        D, H = self.text_proj.out_features, self.cross_attn.num_heads
+        if D // H != 64:
+            raise ValueError("the attention kernel is specialised for head_dim = 64")
+        w = self._pack(hidden_states.device)
+        f = lambda t: t.detach().float()
+        lead = hidden_states.shape[:-1]
+        x = hidden_states.reshape(-1, hidden_states.shape[-1]).to(torch.bfloat16).contiguous()
+        tab = encoder_hidden_states[0].to(torch.bfloat16).contiguous()
+        S = tab.shape[0]
+        h = ops.gemm(x, w["tp"], bias=f(self.text_proj.bias))
+        e = ops.gemm(tab, w["ip"], bias=f(self.image_proj.bias))
+        kv_in = ops.layernorm(e, f(self.norm1.weight), f(self.norm1.bias), self.norm1.eps)
+        hq = ops.layernorm(h, f(self.norm2.weight), f(self.norm2.bias), self.norm2.eps)
+        bias_in = f(self.cross_attn.in_proj_bias)
+        q = ops.gemm(hq, w["wq"], bias=bias_in[:D].contiguous())
+        kv = ops.gemm(kv_in, w["wkv"], bias=bias_in[D:].contiguous())  # [S, 2D] = [K | V]
+        att = ops.attention_1q(q, kv, kv[:, D:], S, H, kv_row_stride=2 * D, kv_batch_stride=0)
+        h2 = ops.gemm(att, w["wo"], bias=f(self.cross_attn.out_proj.bias), residual=hq)
+        z = ops.layernorm(h2, f(self.norm3.weight), f(self.norm3.bias), self.norm3.eps)
+        z = ops.gemm(z, w["w1"], bias=f(self.mlp[0].bias), act=N.ACT_GELU_ERF)
+        out = ops.gemm(z, w["w2"], bias=f(self.mlp[2].bias), residual=h2)
+        return out.float().view(*lead, D)
+

@@ -150,9 +150,6 @@ class CLIPWithAdapters(nn.Module):
 
     def get_text_features(self, input_ids, attention_mask):
         """Text features with adapter: fp32 [B, P] (reference: model_m.py:77-105)."""
-        if self.use_shared_adapters:
-            # raise through the adapter so the message names the missing kernel
-            self.shared_adapters[0](None, None)
         bb = self._backbone()
         input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
         hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
@@ -169,6 +166,13 @@ class CLIPWithAdapters(nn.Module):
         tok0 = ops.layernorm_rows_f32(hidden, bb.final_ln_w, bb.final_ln_b, bb.eps_t, rows=B, ldx=S * bb.Dt)
         if self.use_text_adapter:
             tok0 = self.text_adapter(tok0)
+        if self.use_shared_adapters:
+            # model_m.py:93-100: every shared adapter attends from the text states to the vision position table; each
+            # text row does so on its own and only token 0 is kept (model_m.py:102), so token 0 alone is evaluated.
+            # Inference only: the adapter raises in training mode (no backward kernels for it).
+            table = self.clip.vision_model.embeddings.position_embedding.weight.unsqueeze(0)
+            for shared_adapter in self.shared_adapters:
+                tok0 = shared_adapter(tok0.unsqueeze(1), table).squeeze(1)
         return ops.linear_f32(tok0, bb.text_projection)
 
     def get_image_features(self, pixel_values):
@@ -255,8 +259,6 @@ class CLIPWithAdapters(nn.Module):
         `DevicePrefetcher`'s copy event) lets the towers of step i+1 start while the caller's stream still runs the
         latency-bound adapter backward / AdamW of step i; without it they wait for the caller's stream.
         """
-        if self.use_shared_adapters:
-            self.shared_adapters[0](None, None)
         bb = self._backbone()
         main = torch.cuda.current_stream()
         if self._tower_streams is None:

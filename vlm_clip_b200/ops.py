@@ -268,6 +268,21 @@ def attention(qkv, B: int, S: int, H: int, causal=False, key_mask=None, scale=No
 
 
 @_traced
+def attention_1q(q, k, v, S: int, H: int, kv_row_stride: int, kv_batch_stride: int = 0, q_stride=None, scale=None):
+    """One query row per batch element against S keys (head_dim 64): q bf16 [B, H*64] (row stride q_stride), k / v bf16
+    views whose key j of batch b sits at b*kv_batch_stride + j*kv_row_stride (0 = keys shared by the batch)."""
+    _req(q.dtype == bf16 and k.dtype == bf16 and v.dtype == bf16, "attention_1q: bf16 operands")
+    B = q.shape[0]
+    out = torch.empty((B, H * 64), device=q.device, dtype=bf16)
+    N.check(
+        N.load().vlmclip_attention_1q(N.ptr(q), int(q_stride if q_stride is not None else q.stride(0)), N.ptr(k), N.ptr(v),
+                                      int(kv_row_stride), int(kv_batch_stride), N.ptr(out), B, int(S), int(H),
+                                      float(scale if scale is not None else 64 ** -0.5), N.stream()),
+        "vlmclip_attention_1q")
+    return out
+
+
+@_traced
 def gather_rows_f32(x, rows: int, ld: int, D: int):
     """y[r] = float(x.flat[r*ld : r*ld + D]) — the token-0 slice of a [B*S, D] bf16 activation."""
     out = torch.empty((rows, D), device=x.device, dtype=f32)
