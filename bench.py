@@ -260,9 +260,12 @@ def run_native_arm(args):
 
     # ---------------- opt-in shortcut variant (reported beside the headline, never as it) ----------------
     # Track M pools the causal text tower at token 0 (the reference's BOS quirk), so the text tower on
-    # that single token gives identical features; `value` above is the DENSE computation, this is the same step with
-    # the flag on and the skipped FLOPs taken out of its TFLOP count.
+    # that single token gives identical features, and it keeps only the CLS row of the vision tower's output
+    # (model_m.py:122), so the last vision layer only needs that row after its QKV GEMM; `value` above is the DENSE
+    # computation, this is the same step with both flags on and the skipped FLOPs taken out of its TFLOP count
+    # (SURVEY.md 8d).
     model.text_token0_only = True
+    model.vision_cls_only_last_layer = True
     Ks = max(3, K // 4)
     for i in range(3):
         trainer.training_step(resident[i % nrot])
@@ -275,6 +278,7 @@ def run_native_arm(args):
     barrier()
     ms_short = max_over_ranks(e4.elapsed_time(e5)) / Ks
     model.text_token0_only = False
+    model.vision_cls_only_last_layer = False
 
     # ---------------- roofline of the dominant kernel (instrumented step) ----------------
     # (towers serialised on one stream for this step only, so that a launch's event pair brackets that kernel alone)
@@ -321,10 +325,12 @@ def run_native_arm(args):
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(n1 - n0),
         "shortcut_variant": {
-            "what": "text tower evaluated on token 0 only (result-identical for Track M's BOS pooling under the causal mask); "
-                    "opt-in flag model.text_token0_only, OFF for every other number in this line",
+            "what": "text tower evaluated on token 0 only (result-identical for Track M's BOS pooling under the causal mask) and "
+                    "last vision layer evaluated for the CLS row only after its QKV GEMM; opt-in flags "
+                    "model.text_token0_only / model.vision_cls_only_last_layer, OFF for every other number in this line",
             "value": world * BATCH / (ms_short / 1e3), "unit": UNIT, "ms_per_step": ms_short, "steps": Ks,
-            "executed_tflop_per_step_per_gpu": (fl["image"] * BATCH + fl["caption"] * BATCH / 77.0) / 1e12,
+            "executed_tflop_per_step_per_gpu": ((fl["image"] - _cls_only_skipped_flops(MODEL)) * BATCH
+                                                + fl["caption"] * BATCH / 77.0) / 1e12,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
@@ -339,6 +345,15 @@ def run_native_arm(args):
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cls_only_skipped_flops(model_name: str) -> float:
+    """FLOPs of the last vision layer that the CLS-only evaluation does not execute (per image)."""
+    from oracle import clip_oracle as O
+
+    v = O.CLIP_DIMS[model_name].vision
+    S, D, F = v.seq, v.width, v.mlp
+    return float((S - 1) * (2 * D * D + 4 * D * F) + 4 * (S - 1) * S * D)
 
 
 _JSON_OUT = None

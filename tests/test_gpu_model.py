@@ -252,6 +252,14 @@ def test_text_token0_shortcut_is_result_preserving(cuda, clip_b32):
     assert _rel(short["text_features"], dense["text_features"]) < 1e-5
     assert abs(short["loss"].item() - dense["loss"].item()) < 1e-5
     assert torch.equal(short["logits_per_image"].argmax(1), dense["logits_per_image"].argmax(1))
+    # image side: last vision layer for the CLS row only (single-query attention instead of the tile kernel)
+    model.text_token0_only = False
+    model.vision_cls_only_last_layer = True
+    with torch.no_grad():
+        cls = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    assert _rel(cls["image_features"], dense["image_features"]) < 5e-3
+    assert abs(cls["loss"].item() - dense["loss"].item()) < 1e-3
+    assert torch.equal(cls["logits_per_image"].argmax(1), dense["logits_per_image"].argmax(1))
 
 
 def test_config3_vit_l14_dims_with_peclip_adapters(cuda):

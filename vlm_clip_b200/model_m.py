@@ -112,6 +112,9 @@ class CLIPWithAdapters(nn.Module):
         # reference's BOS quirk) and the text tower is causal, so the pooled state depends on token 0 alone; with this
         # flag the text tower runs on that one token per caption.  Off by default: the dense tower is the benchmark.
         self.text_token0_only = False
+        # Same kind of opt-in shortcut for the image side: the last vision layer evaluated for the CLS row only
+        # (model_m.py:122 keeps last_hidden_state[:, 0]); needs the LN-folded towers.
+        self.vision_cls_only_last_layer = False
         # on-GPU preprocessing of uint8 frames (extension): CLIP's normalisation by default, RGB channel order
         self.pixel_mean, self.pixel_std, self.frames_bgr = CLIP_MEAN, CLIP_STD, False
 
@@ -181,8 +184,8 @@ class CLIPWithAdapters(nn.Module):
         `pixel_values`: float [B, 3, H, W] as in the reference, or (extension) decoded uint8 frames [B, Hs, Ws, 3], which
         are resized / scaled / normalised on the GPU (`self.pixel_mean`, `self.pixel_std`, `self.frames_bgr`)."""
         bb = self._backbone()
-        hidden, n = self._vision_hidden(bb, pixel_values)
-        return self._image_head(bb, hidden, n)
+        hidden, n, seq = self._vision_hidden(bb, pixel_values)
+        return self._image_head(bb, hidden, n, seq)
 
     def get_video_features(self, clips):
         """Clip features: fp32 [B, P] = get_image_features(frames).view(B, T, P).mean(1) (the reference
@@ -192,26 +195,29 @@ class CLIPWithAdapters(nn.Module):
             raise ValueError("clips must be [B, 3, T, H, W] float or [B, T, Hs, Ws, 3] uint8")
         T = clips.shape[1] if clips.dtype == torch.uint8 else clips.shape[2]
         bb = self._backbone()
-        hidden, n = self._vision_hidden(bb, clips)
-        return ops.mean_pool(self._image_head(bb, hidden, n), T)
+        hidden, n, seq = self._vision_hidden(bb, clips)
+        return ops.mean_pool(self._image_head(bb, hidden, n, seq), T)
 
     def _vision_hidden(self, bb, pixel_values):
-        """Tower output for any accepted pixel layout -> (bf16 [n*S, D], n images)."""
+        """Tower output for any accepted pixel layout -> (bf16 [n*seq, D], n images, seq rows per image kept)."""
+        cls_only = self.vision_cls_only_last_layer and bb.fold_ln
+        seq = 1 if cls_only else bb.Sv
         if pixel_values.dtype == torch.uint8:
             if pixel_values.dim() not in (4, 5) or pixel_values.shape[-1] != 3:
                 raise ValueError("uint8 frames must be [B, Hs, Ws, 3] or [B, T, Hs, Ws, 3]")
             n = pixel_values.numel() // (pixel_values.shape[-3] * pixel_values.shape[-2] * 3)
-            return bb.vision_hidden_u8(pixel_values, self.pixel_mean, self.pixel_std, self.frames_bgr), n
+            return bb.vision_hidden_u8(pixel_values, self.pixel_mean, self.pixel_std, self.frames_bgr, cls_only), n, seq
         if pixel_values.dim() == 5:  # [B, 3, T, H, W] -> [B*T, 3, H, W] (a layout copy, as the reference's caller would do)
             B, C, T, H, W = pixel_values.shape
             pixel_values = pixel_values.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
-        return bb.vision_hidden(pixel_values), pixel_values.shape[0]
+        return bb.vision_hidden(pixel_values, cls_only), pixel_values.shape[0], seq
 
-    def _image_head(self, bb, hidden, B):
+    def _image_head(self, bb, hidden, B, seq=None):
+        seq = bb.Sv if seq is None else seq
         if self.use_vision_adapter:
-            cls = self.vision_adapter.forward_token0(hidden, B, bb.Sv)
+            cls = self.vision_adapter.forward_token0(hidden, B, seq)
         else:
-            cls = ops.gather_rows_f32(hidden, B, bb.Sv * bb.Dv, bb.Dv)
+            cls = ops.gather_rows_f32(hidden, B, seq * bb.Dv, bb.Dv)
         return ops.linear_f32(cls, bb.visual_projection)
 
     def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True, *, inputs_ready=None):
@@ -274,7 +280,7 @@ class CLIPWithAdapters(nn.Module):
         with torch.cuda.stream(txt):
             t_hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)
         with torch.cuda.stream(vis):
-            v_hidden, n_img = self._vision_hidden(bb, pixel_values)
+            v_hidden, n_img, v_seq = self._vision_hidden(bb, pixel_values)
         input_ids.record_stream(txt)
         if attention_mask is not None:
             attention_mask.record_stream(txt)
@@ -284,7 +290,7 @@ class CLIPWithAdapters(nn.Module):
         t_hidden.record_stream(main)
         v_hidden.record_stream(main)
         text_features = self._text_head(bb, t_hidden, input_ids.shape[0], input_ids.shape[1])
-        image_features = self._image_head(bb, v_hidden, n_img)
+        image_features = self._image_head(bb, v_hidden, n_img, v_seq)
         if pixel_values.dim() == 5:  # clips: temporal mean-pool of the per-frame features
             image_features = ops.mean_pool(image_features, n_img // pixel_values.shape[0])
         return text_features, image_features

@@ -155,7 +155,9 @@ class NativeClipTowers:
         return tab
 
     def _encoder(self, x: torch.Tensor, layers: List[_Layer], B: int, S: int, H: int, eps: float, causal: bool,
-                 key_mask: Optional[torch.Tensor]) -> torch.Tensor:
+                 key_mask: Optional[torch.Tensor], cls_only: bool = False) -> torch.Tensor:
+        """All encoder layers over the residual stream x [B*S, D] (in place).  `cls_only` (vision, LN folded): the last
+        layer is evaluated for token 0 of every sequence only and [B, D] is returned (see `_last_layer_cls`)."""
         M, D = x.shape
         F = layers[0].fc1_w.shape[0]
         dev = x.device
@@ -167,14 +169,20 @@ class NativeClipTowers:
         # x (out-proj / fc2); a 5 MB combine pass turns them into (mean, rstd) instead of re-reading the 77 MB stream
         part = torch.empty((M, D // 32, 2), device=dev, dtype=f32)
         xn = None if self.fold_ln else torch.empty((M, D), device=dev, dtype=bf16)
-        if self.fold_ln and ops.TRACE is None and ops.PROFILE is None and not _STATS_IN_GEMM:
+        if cls_only and not (self.fold_ln and not causal and key_mask is None):
+            raise N.NativeError("cls_only needs the LN-folded, unmasked (vision) encoder")
+        if self.fold_ln and (cls_only or (ops.TRACE is None and ops.PROFILE is None and not _STATS_IN_GEMM)):
             # the whole tower in one native call (same kernels, same order as the loop below: that loop stays as the
             # per-op path the tracing / roofline hooks time)
-            table = self._layer_table(layers)
-            N.check(
-                N.load().vlmclip_encoder_fwd(table, len(layers), N.ptr(x), N.ptr(qkv), N.ptr(att), N.ptr(hid), N.ptr(stats),
-                                             N.ptr(part), N.ptr(key_mask), B, S, H, D, F, float(eps), 1 if causal else 0,
-                                             N.ACT_QUICK_GELU, N.stream()), "vlmclip_encoder_fwd")
+            n_full = len(layers) - 1 if cls_only else len(layers)
+            if n_full > 0:
+                table = self._layer_table(layers)
+                N.check(
+                    N.load().vlmclip_encoder_fwd(table, n_full, N.ptr(x), N.ptr(qkv), N.ptr(att), N.ptr(hid), N.ptr(stats),
+                                                 N.ptr(part), N.ptr(key_mask), B, S, H, D, F, float(eps),
+                                                 1 if causal else 0, N.ACT_QUICK_GELU, N.stream()), "vlmclip_encoder_fwd")
+            if cls_only:
+                return self._last_layer_cls(x, layers[-1], B, S, H, eps, qkv, stats, part, first=n_full == 0)
             return x
         first = True
         for L in layers:
@@ -206,10 +214,31 @@ class NativeClipTowers:
             ops.gemm(hid, L.fc2_w, bias=L.fc2_b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
         return x
 
+    def _last_layer_cls(self, x, L: _Layer, B: int, S: int, H: int, eps: float, qkv, stats, part, first: bool):
+        """Last encoder layer for token 0 only -> bf16 [B, D] = last_hidden_state[:, 0].
+
+        Result-preserving: Track M keeps `last_hidden_state[:, 0]` (model_m.py:122), and within a layer
+        token 0 needs every token's K and V but only its own Q, attention row, out-proj, LN2 and MLP.  The QKV GEMM
+        still runs on all tokens; everything after it runs on B rows."""
+        D = x.shape[1]
+        if first:
+            ops.row_stats(x, eps, out=stats)
+        else:
+            ops.ln_partials_to_stats(part, eps, out=stats)
+        ops.gemm(x, L.qkv_w, bias=L.qkv_b, row_stats=stats, col_c=L.qkv_c, out=qkv)
+        q0 = qkv.view(B, S, 3 * D)[:, 0, :D]  # row stride S*3D
+        att0 = ops.attention_1q(q0, qkv[:, D:2 * D], qkv[:, 2 * D:], S, H, kv_row_stride=3 * D, kv_batch_stride=S * 3 * D)
+        x0 = x.view(B, S, D)[:, 0]  # row stride S*D
+        y0 = ops.gemm(att0, L.out_w, bias=L.out_b, residual=x0)
+        st0 = ops.row_stats(y0, eps)
+        h0 = ops.gemm(y0, L.fc1_w, bias=L.fc1_b, row_stats=st0, col_c=L.fc1_c, act=N.ACT_QUICK_GELU)
+        return ops.gemm(h0, L.fc2_w, bias=L.fc2_b, residual=y0, out=y0)
+
     # ------------------------------------------------------------------------------------------ towers
     @torch.no_grad()
-    def vision_hidden(self, pixel_values: torch.Tensor) -> torch.Tensor:
-        """`vision_model(pixel_values).last_hidden_state` as bf16 [B*S, D] (NOT through post_layernorm, HF:684)."""
+    def vision_hidden(self, pixel_values: torch.Tensor, cls_only: bool = False) -> torch.Tensor:
+        """`vision_model(pixel_values).last_hidden_state` as bf16 [B*S, D] (NOT through post_layernorm, HF:684);
+        with `cls_only` just its token-0 rows, bf16 [B, D]."""
         if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
             raise ValueError("pixel_values must be [B, 3, H, W]")
         if pixel_values.shape[2] != self.image or pixel_values.shape[3] != self.image:
@@ -219,15 +248,15 @@ class NativeClipTowers:
             pixel_values = pixel_values.float()
         pixel_values = pixel_values.contiguous()
         B = pixel_values.shape[0]
-        return self._vision_from_cols(ops.im2col(pixel_values, self.patch), B)
+        return self._vision_from_cols(ops.im2col(pixel_values, self.patch), B, cls_only)
 
-    def _vision_from_cols(self, cols: torch.Tensor, B: int) -> torch.Tensor:
+    def _vision_from_cols(self, cols: torch.Tensor, B: int, cls_only: bool = False) -> torch.Tensor:
         patches = ops.gemm(cols, self.patch_w)  # [B*np, D] bf16 (staged TMA epilogue; the fp32 path costs 2x the traffic)
         x = ops.vision_embed_ln(patches, self.cls, self.pos_v, self.pre_ln_w, self.pre_ln_b, B, self.Sv, self.eps_v)
-        return self._encoder(x, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None)
+        return self._encoder(x, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None, cls_only)
 
     @torch.no_grad()
-    def vision_hidden_u8(self, frames_u8: torch.Tensor, mean, std, bgr: bool = False) -> torch.Tensor:
+    def vision_hidden_u8(self, frames_u8: torch.Tensor, mean, std, bgr: bool = False, cls_only: bool = False) -> torch.Tensor:
         """Same as `vision_hidden`, from decoded uint8 frames [..., Hs, Ws, 3]: resize to the model resolution, /255 and
         normalisation are fused into the patch extraction (process_video.py:14-29 semantics; `vlmclip_preprocess_patches`)."""
         if frames_u8.dtype != torch.uint8 or frames_u8.dim() < 4 or frames_u8.shape[-1] != 3:
@@ -235,7 +264,7 @@ class NativeClipTowers:
         frames_u8 = frames_u8.contiguous()
         n = frames_u8.numel() // (frames_u8.shape[-3] * frames_u8.shape[-2] * 3)
         cols = ops.preprocess_patches(frames_u8, self.image, self.image, self.patch, mean, std, bgr)
-        return self._vision_from_cols(cols, n)
+        return self._vision_from_cols(cols, n, cls_only)
 
     @torch.no_grad()
     def text_hidden_pre_ln(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
