@@ -247,9 +247,15 @@ vision_embed_ln_kernel(const void* __restrict__ patch_v, const float* __restrict
   for (int i = 0; i < NV; ++i) {
     if (valid[i]) {
       const int c = (lane + i * 32) * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, __ldg(gamma + c + j), __ldg(beta + c + j));
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gv[j], bv[j]);
       st_v4(yr + c, pack8(o));
     }
   }
@@ -434,7 +440,7 @@ extern "C" int vlmclip_vision_embed_ln(const void* patch, int patch_bf16, const 
   VLMCLIP_CHECK_ARG(patch && cls && pos && gamma && beta && y, "vision_embed_ln: null pointer");
   VLMCLIP_CHECK_ARG(B > 0 && S > 1 && D % 8 == 0 && D <= MAX_VEC * 256, "vision_embed_ln: bad dims B=%d S=%d D=%d", B, S, D);
   VLMCLIP_CHECK_ARG((uintptr_t)patch % 16 == 0 && (uintptr_t)cls % 16 == 0 && (uintptr_t)pos % 16 == 0 &&
-                        (uintptr_t)y % 16 == 0,
+                        (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0,
                     "vision_embed_ln: pointers must be 16-byte aligned");
   const int64_t rows = (int64_t)B * S;
   const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
