@@ -739,6 +739,10 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   if (pair) {
     rc = make_tmap_bf16(&tmB, W, N, K, ldw, 128);  // each CTA of the pair loads 128 of the 256 W rows of a tile
     if (rc) return rc;
+    // short-K residual GEMMs (out-proj) wait on their residual panels (TMA store -> read-done -> TMA load chain): four
+    // panels per epilogue group instead of two, paid for with one pipeline stage (measured 65.8 -> 62.6 us; with K = 3072
+    // the deeper pipeline wins, 165.6 vs 168.2 us)
+    if (epi == EPI_RES && K <= 1024 && cfg_override != 62) return launch_gemm<256, 5, 4, true, EPI_RES>(tmA, tmB, tmC, tmR, p, s);
     VLMCLIP_GEMM_LAUNCH(256, 6, 2, true)
   }
   if (wide) {
