@@ -39,6 +39,10 @@ METRIC = "adapter fine-tune images/sec (ViT-B/16, bf16)"
 UNIT = "images/s"
 
 
+WORKLOAD = ("CLIP ViT-B/16 + bottleneck adapters (A=256), frozen backbone, Track-M train step "
+            "(fwd both towers, global InfoNCE, adapter bwd, clip + AdamW)")
+
+
 def _peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -98,7 +102,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": mean_t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CLIP ViT-B/16 + bottleneck adapters (A=256), Track-M train step, CPU sample of 8 pairs"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * max(1, args.gpus),
+                   "parallelism": f"dp{max(1, args.gpus)}",
+                   "sample": "each step is a bounded sample of the workload: 8 of the 256 pairs, same model, same step "
+                             "(forward both towers, InfoNCE, adapter backward, clip_grad_norm, AdamW), fp32 on the host cores; "
+                             "images/s is linear in the batch on the CPU"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -307,8 +315,7 @@ def run_native_arm(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {
-            "workload": "CLIP ViT-B/16 + bottleneck adapters (A=256), frozen backbone, Track-M train step "
-                        "(fwd both towers, global InfoNCE, adapter bwd, clip + AdamW)",
+            "workload": WORKLOAD,
             "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
             "init": "random (seed 0), no checkpoints offline",
             "l2": "3 rotating input batches; 154 MB pixel batch and >1 GB of activations per step exceed the 126 MB L2",
