@@ -269,6 +269,8 @@ class CLIPWithAdapters(nn.Module):
         main = torch.cuda.current_stream()
         if self._tower_streams is None:
             dev = pixel_values.device
+            # default priority on purpose: high-priority tower streams starve the caller's stream (measured 11.8 vs
+            # 11.6 ms per step), a high-priority caller's stream changes nothing (tools/overlap_ab.py)
             self._tower_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         vis, txt = self._tower_streams
         for st in (vis, txt):
