@@ -337,3 +337,38 @@ def test_shared_mhs_adapter_inference(cuda, clip_b32):
         hid = O.shared_mhs_adapter(hid, tab, {k: v.detach() for k, v in ad.state_dict().items()})
     ref_t = hid[:, 0] @ sd["text_projection.weight"].t()
     assert _rel(t, ref_t) < FEAT_TOL, _rel(t, ref_t)
+
+
+def test_full_size_properties_vit_b16_batch256(cuda):
+    """BASELINE config 2 at full size (ViT-B/16, 256 pairs), checked through size-independent properties instead of the
+    oracle (a fp32 CPU pass at this size takes minutes): (1) every caption starts with BOS and the text tower is causal,
+    so all text rows coincide and the symmetric InfoNCE loss is ln(256); (2) the step is deterministic
+    (no atomics, fixed reduction orders): two runs are bit identical; (3) permuting the batch permutes the image
+    features; (4) only adapter parameters receive gradients and they are finite."""
+    B16 = "openai/clip-vit-base-patch16"
+    clip = O.build_hf_clip(B16, seed=0).to(cuda)
+    for p_ in clip.parameters():
+        p_.requires_grad_(False)
+    model = _make_model(cuda, clip)
+    model.train()
+    Bn = 256
+    pix, ids, mask = O.synthetic_batch(Bn, seed=2)
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    out1 = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    out1["loss"].backward()
+    g1 = [p_.grad.clone() for p_ in model.parameters() if p_.requires_grad]
+    assert abs(out1["loss"].item() - math.log(Bn)) < 2e-3, out1["loss"].item()
+    assert (out1["text_features"] - out1["text_features"][0]).abs().max().item() == 0.0
+    assert all(torch.isfinite(g).all() for g in g1) and len(g1) == 12
+    assert all(p_.grad is None for p_ in clip.parameters())
+    model.zero_grad(set_to_none=True)
+    out2 = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    out2["loss"].backward()
+    g2 = [p_.grad.clone() for p_ in model.parameters() if p_.requires_grad]
+    assert torch.equal(out1["image_features"], out2["image_features"]) and torch.equal(out1["loss"], out2["loss"])
+    assert all(torch.equal(a, b) for a, b in zip(g1, g2))
+    perm = torch.randperm(Bn, generator=torch.Generator().manual_seed(0)).to(cuda)
+    with torch.no_grad():
+        f = model.get_image_features(pix)
+        fp = model.get_image_features(pix[perm].contiguous())
+    assert torch.equal(fp, f[perm])
