@@ -677,6 +677,8 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
     const long t256 = (long)p.m_tiles * ((N + 255) / 256), t128 = (long)p.m_tiles * ((N + 127) / 128);
     const double c256 = (double)((t256 + sms - 1) / sms), c128 = 0.56 * (double)((t128 + sms - 1) / sms);
     if (c128 < 0.92 * c256) wide = false;
+    const char* force = getenv("VLMCLIP_GEMM_NARROW");  // experiment switch
+    if (force != nullptr && force[0] == '1') wide = false;
   }
   const int block_n = wide ? 256 : 128;
   p.staged = out_fp32 ? 0 : 1;
