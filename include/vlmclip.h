@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VLMCLIP_ABI_VERSION 1
+#define VLMCLIP_ABI_VERSION 2
 
 /* activation selector for GEMM epilogues and adapter kernels */
 enum {

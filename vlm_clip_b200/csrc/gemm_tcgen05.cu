@@ -3,21 +3,27 @@
 // Replaces the aten::addmm calls behind nn.Linear at HF modeling_clip.py:310-312,334 (q/k/v/out),
 // :348-350 (fc1 / quick_gelu / fc2) and :209 (patch conv as GEMM).
 //
-// B200 design (one CTA per SM, persistent over output tiles):
-//   warp 0 (1 thread)  TMA producer: A tile [128 x 64] and W tile [BLOCK_N x 64] per stage,
+// B200 design (persistent over output tiles; one CTA per SM, normally as 2-CTA clusters):
+//   PAIR               two CTAs of a cluster share one 256 x 256 tile: each loads its 128 A rows and HALF of the W rows,
+//                      the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) for both and multicasts the commits, so
+//                      every SM pulls half the W bytes through shared memory.  Single-CTA variants (128 x 256,
+//                      128 x 128) remain for M <= 128.
+//   warp 0 (1 thread)  TMA producer: A tile [128 x 64] and W tile [BLOCK_N(/2) x 64] per stage,
 //                      128-byte swizzle, completion by mbarrier complete_tx.
-//   warp 1 (1 thread)  tcgen05.mma issuer (cta_group::1, M=128, N=BLOCK_N, K=16 x 4 per stage),
-//                      fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the
-//                      epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 1 (1 thread)  tcgen05.mma issuer (K = 16 x 4 per stage), fp32 accumulators in TMEM, double buffered
+//                      (2 x BLOCK_N columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 //   warp 2             TMEM allocator / deallocator; lane 0 = panel manager of epilogue group 0.
 //   warp 3 (1 thread)  panel manager of epilogue group 1.
 //   warps 4..11        epilogue, two groups of 4 warps (each group covers the 128 accumulator rows and
 //                      owns every other 64-column quarter of the tile): tcgen05.ld -> registers ->
 //                      LN-fold / bias / activation (vectors staged in smem once per tile) -> + residual
-//                      (prefetched by TMA into a 128-B-swizzled 128x64 panel) -> bf16 written in place
+//                      (prefetched by TMA into a 64-B-swizzled 128 x 32 panel) -> bf16 written in place
 //                      into the panel -> TMA store.  Panel managers chain store -> wait-read -> next
 //                      residual load so global traffic of the epilogue is fully asynchronous.
+//   EPI                the epilogue is specialised at compile time (fold / fold+gelu / residual / plain / generic):
+//                      the fully unrolled run-time-switched version thrashed the instruction cache.
 //   Tile order is n-fastest so the CTAs running at one moment share a few A row-blocks through L2.
+//   Launched with programmatic dependent launch: the prologue overlaps the previous kernel's tail.
 #include <cstdio>
 #include <cstdlib>
 
