@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VLMCLIP_ABI_VERSION 2
+#define VLMCLIP_ABI_VERSION 3
 
 /* activation selector for GEMM epilogues and adapter kernels */
 enum {
@@ -233,6 +233,50 @@ int vlmclip_adamw_clip_step(float* params, const float* grads, float* exp_avg, f
                             const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
                             float max_norm, int32_t* step, float* grad_norm_out, float* workspace,
                             void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backbone backward (full fine-tune, BASELINE config 5: `CLIPWithAdapters(freeze_clip=False)`, model_m.py:22,72-75).
+ * The reference gets these from autograd over HF modeling_clip.py; here every dense product is put into the
+ * C = A W^T form of vlmclip_gemm_bf16 (dgrad: A = dY, W = W^T; wgrad: A = dY^T, W = X^T, fp32 output) by the
+ * transposes below, and the row-wise pieces are the kernels of csrc/backward.cu / csrc/attention_bwd.cu.
+ * --------------------------------------------------------------------------------------------------------- */
+/* dst[c, r] = bf16(src[row(r), c]), r < R; dst[c, R..Rpad) = 0 (Rpad: the GEMM's K, a multiple of 8).  src is fp32
+ * (src_f32 = 1: a master weight) or bf16 (an activation / gradient), [.., C] with lds; dst bf16 [C, ldd].
+ * Row gather (group_dst > 0): row(r) = (r / group_dst) * group_src + group_off + r % group_dst, e.g. (S-1, S, 1)
+ * drops the CLS row of every image (patch-embedding weight gradient, HF:209). */
+int vlmclip_transpose_to_bf16(const void* src, int src_f32, int64_t lds, void* dst, int64_t ldd, int R, int Rpad, int C,
+                              int group_dst, int group_src, int group_off, void* stream);
+/* fp32 -> bf16 (per-step cast of the trainable master weights, and of the fp32 gradient stream for the next GEMM) */
+int vlmclip_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* out[r] = sum_c x[r, c], x bf16 [R, C] (ldx): bias gradient = row sums of the transposed output gradient */
+int vlmclip_rowsum_bf16(const void* x, int64_t ldx, float* out, int R, int C, void* stream);
+/* out[c] = sum_r x[r*ldx + c], fp32: position / class embedding gradients (sum over the batch), HF:214-217,255-256 */
+int vlmclip_colsum_f32(const float* x, int64_t ldx, float* out, int R, int64_t C, void* stream);
+/* quick_gelu (HF:349) as a stand-alone op (training keeps the pre-activation) and its backward da = dy * g'(a) */
+int vlmclip_quick_gelu_bf16(const void* a, void* y, int64_t n, void* stream);
+int vlmclip_quick_gelu_bwd_bf16(const void* a, const void* dy, void* da, int64_t n, void* stream);
+/* LayerNorm backward (HF:371,380,562,677; adapter LN is handled inside vlmclip_adapter_bwd).
+ *   x: the bf16 INPUT of the LayerNorm [M, D] (ldx; statistics are recomputed from it); dy: gradient of its output,
+ *   bf16 (dy_f32 = 0) or fp32 (dy_f32 = 1), lddy.  dres (optional, fp32, lddx): gradient arriving over the skip
+ *   connection, added to dx.  dx is written as fp32 (dx_f32) and / or bf16 (dx_bf16), both with lddx.
+ *   dgamma / dbeta fp32 [D] (optional, WRITTEN); workspace: vlmclip_layernorm_bwd_workspace(M, D) floats. */
+int64_t vlmclip_layernorm_bwd_workspace(int M, int D);
+int vlmclip_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
+                          const float* dres, float* dx_f32, void* dx_bf16, int64_t lddx, float* dgamma, float* dbeta,
+                          float* workspace, int M, int D, float eps, void* stream);
+/* Vision tokens without pre_layrnorm (HF:211-218): e[b,0] = cls + pos[0]; e[b,1+p] = patch[b,p] + pos[1+p], bf16.
+ * Training keeps e as the saved input of the pre-LayerNorm. */
+int vlmclip_vision_embed(const void* patch, const float* cls, const float* pos, void* e, int B, int S, int D,
+                         void* stream);
+/* token_embedding.weight gradient (HF:248): dtok[ids[r]] += d[r] (fp32 atomics; dtok zeroed by the caller) */
+int vlmclip_embed_scatter_add(const float* d, int64_t ldd, const int64_t* ids, float* dtok, int64_t rows, int D, int V,
+                              void* stream);
+/* Backward of vlmclip_attention_fwd: dqkv [B*S, 3D] (bf16, WRITTEN) from qkv, out = forward output [B*S, D] and its
+ * gradient dout.  Probabilities are recomputed (nothing else is kept from the forward).  S <= 288, head_dim 64. */
+int vlmclip_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask, int B,
+                          int S, int H, int causal, float scale, void* stream);
+/* dW[N,K] = dy[R,N]^T x[R,K] (fp32): weight gradient of vlmclip_linear_f32 when the projection is trainable */
+int vlmclip_linear_f32_wgrad(const float* dy, const float* x, int64_t ldx, float* dW, int R, int N, int K, void* stream);
 
 /* bf16 <-> fp32 casts with optional row gather (token-0 slice): y[r, :] = x[r*ldx : r*ldx + D] */
 int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream);

@@ -1,0 +1,204 @@
+"""Kernel-level parity of the backbone-backward entry points (full fine-tune, BASELINE config 5) against torch
+autograd in fp32 on the same (bf16-rounded) inputs.  Tolerances next to each check: outputs are bf16 (2^-9 relative
+rounding) unless noted."""
+import math
+
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+pytestmark = pytest.mark.gpu
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("R,C,src_f32", [(50, 72, False), (197 * 3, 768, False), (512, 2048, True), (33, 40, True)])
+def test_transpose_pad(cuda, R, C, src_f32):
+    from vlm_clip_b200 import ops
+
+    x = torch.randn(R, C, device=cuda, generator=_gen(R + C))
+    src = x if src_f32 else x.to(bf16)
+    out = ops.transpose_bf16(src)
+    Rpad = (R + 7) // 8 * 8
+    assert out.shape == (C, Rpad)
+    assert torch.equal(out[:, :R], src.to(bf16).t())  # bit exact: a layout change plus one rounding
+    assert (out[:, R:] == 0).all()
+
+
+def test_transpose_row_gather(cuda):
+    from vlm_clip_b200 import ops
+
+    B, S, D = 3, 50, 64
+    x = torch.randn(B * S, D, device=cuda, generator=_gen(1)).to(bf16)
+    out = ops.transpose_bf16(x, gather=(S - 1, S, 1))  # drop the CLS row of every image
+    ref = x.view(B, S, D)[:, 1:].reshape(B * (S - 1), D).t()
+    assert torch.equal(out[:, : B * (S - 1)], ref)
+    assert (out[:, B * (S - 1):] == 0).all()
+
+
+def test_cast_rowsum_colsum(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(3)
+    w = torch.randn(768, 516, device=cuda, generator=g)
+    assert torch.equal(ops.cast_bf16(w), w.to(bf16))
+    xb = torch.randn(96, 1000, device=cuda, generator=g).to(bf16)
+    assert _rel(ops.rowsum_bf16(xb), xb.float().sum(1)) < 1e-5
+    xf = torch.randn(37, 5000, device=cuda, generator=g)
+    assert _rel(ops.colsum_f32(xf), xf.sum(0)) < 1e-5
+
+
+def test_quick_gelu_fwd_bwd(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(4)
+    a = (torch.randn(64, 3072, device=cuda, generator=g) * 2).to(bf16)
+    dy = torch.randn(64, 3072, device=cuda, generator=g).to(bf16)
+    af = a.float().requires_grad_()
+    y = O.quick_gelu(af)
+    y.backward(dy.float())
+    assert _rel(ops.quick_gelu(a), y) < 4e-3      # bf16 output rounding + tanh.approx
+    assert _rel(ops.quick_gelu_bwd(a, dy), af.grad) < 4e-3
+
+
+@pytest.mark.parametrize("M,D,dy_f32,with_res", [(197 * 4, 768, False, True), (77 * 8, 512, False, False),
+                                                  (300, 1024, False, True), (16, 512, True, False)])
+def test_layernorm_bwd(cuda, M, D, dy_f32, with_res):
+    from vlm_clip_b200 import ops
+
+    g = _gen(M + D)
+    x = (torch.randn(M, D, device=cuda, generator=g) * 1.5 + 0.3).to(bf16)
+    gamma = torch.rand(D, device=cuda, generator=g) + 0.5
+    beta = torch.randn(D, device=cuda, generator=g)
+    dy = torch.randn(M, D, device=cuda, generator=g)
+    dy = dy if dy_f32 else dy.to(bf16)
+    dres = torch.randn(M, D, device=cuda, generator=g) if with_res else None
+    xf = x.float().requires_grad_()
+    gf, bf = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    O.layer_norm(xf, gf, bf).backward(dy.float())
+    ref_dx = xf.grad + (dres if with_res else 0)
+    dx32 = torch.empty(M, D, device=cuda, dtype=f32)
+    dx16 = torch.empty(M, D, device=cuda, dtype=bf16)
+    dgamma, dbeta = ops.layernorm_bwd(dy, x, gamma, 1e-5, dres=dres, dx_f32=dx32, dx_bf16=dx16)
+    assert _rel(dx32, ref_dx) < 1e-5
+    assert _rel(dx16, ref_dx) < 4e-3
+    assert _rel(dgamma, gf.grad) < 1e-5
+    assert _rel(dbeta, bf.grad) < 1e-5
+
+
+def test_layernorm_bwd_strided_rows(cuda):
+    """Token-0 rows of a [B*S, D] buffer (the pooled rows of Track M): strided x and strided dx into a zeroed stream."""
+    from vlm_clip_b200 import ops
+
+    B, S, D = 6, 77, 512
+    g = _gen(9)
+    h = torch.randn(B * S, D, device=cuda, generator=g).to(bf16)
+    gamma = torch.rand(D, device=cuda, generator=g) + 0.5
+    dy = torch.randn(B, D, device=cuda, generator=g)
+    x0 = h.view(B, S * D)[:, :D]
+    dx = torch.zeros(B * S, D, device=cuda, dtype=f32)
+    ops.layernorm_bwd(dy, x0, gamma, 1e-5, dx_f32=dx.view(B, S * D)[:, :D])
+    xf = x0.float().clone().requires_grad_()
+    O.layer_norm(xf, gamma, torch.zeros_like(gamma)).backward(dy)
+    assert _rel(dx.view(B, S, D)[:, 0], xf.grad) < 1e-5
+    assert (dx.view(B, S, D)[:, 1:] == 0).all()
+
+
+def _attn_ref(qkv, B, S, H, causal, key_mask):
+    D = H * 64
+    q, k, v = qkv.view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)  # [B,H,S,64]
+    s = (q @ k.transpose(-1, -2)) * 64 ** -0.5
+    mask = torch.zeros(B, 1, S, S, device=qkv.device, dtype=torch.bool)
+    if causal:
+        mask |= torch.triu(torch.ones(S, S, device=qkv.device, dtype=torch.bool), 1)
+    if key_mask is not None:
+        mask |= (key_mask == 0)[:, None, None, :]
+    s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+
+
+@pytest.mark.parametrize("B,S,H,causal,masked", [(2, 50, 12, False, False), (3, 77, 8, True, False), (2, 77, 8, True, True),
+                                                  (1, 197, 12, False, False), (1, 257, 16, False, False)])
+def test_attention_bwd(cuda, B, S, H, causal, masked):
+    from vlm_clip_b200 import ops
+
+    g = _gen(B * 1000 + S)
+    D = H * 64
+    qkv = torch.randn(B * S, 3 * D, device=cuda, generator=g).to(bf16)
+    dout = torch.randn(B * S, D, device=cuda, generator=g).to(bf16)
+    key_mask = None
+    if masked:
+        key_mask = torch.ones(B, S, device=cuda, dtype=torch.uint8)
+        key_mask[0, 40:] = 0
+        key_mask[1, 60:] = 0
+    qf = qkv.float().requires_grad_()
+    ref_out = _attn_ref(qf, B, S, H, causal, key_mask)
+    ref_out.backward(dout.float())
+    out = ops.attention(qkv, B, S, H, causal=causal, key_mask=key_mask)
+    assert _rel(out, ref_out) < 8e-3
+    dqkv = ops.attention_bwd(qkv, out, dout, B, S, H, causal=causal, key_mask=key_mask)
+    # gradient recomputed in fp32 from bf16 inputs, bf16 output; O (for D_i) carries the forward's bf16 error
+    assert _rel(dqkv[:, :D], qf.grad[:, :D]) < 1e-2
+    assert _rel(dqkv[:, D:2 * D], qf.grad[:, D:2 * D]) < 1e-2
+    assert _rel(dqkv[:, 2 * D:], qf.grad[:, 2 * D:]) < 1e-2
+
+
+def test_dense_layer_backward_through_tn_gemm(cuda):
+    """dgrad / wgrad / bias gradient of y = x W^T + b through the forward GEMM kernel and the transposes."""
+    from vlm_clip_b200 import ops
+
+    M, K, Nn = 197 * 3 + 1, 768, 2304  # M not a multiple of 8: the transposed operands are zero padded
+    g = _gen(11)
+    x = torch.randn(M, K, device=cuda, generator=g).to(bf16)
+    W = (torch.randn(Nn, K, device=cuda, generator=g) / math.sqrt(K))
+    dy = torch.randn(M, Nn, device=cuda, generator=g).to(bf16)
+    Wt = ops.transpose_bf16(W)                      # [K, N] bf16
+    dx = ops.gemm(dy, Wt)                           # [M, K]
+    dyT, xT = ops.transpose_bf16(dy), ops.transpose_bf16(x)
+    dW = ops.gemm(dyT, xT, out_fp32=True)           # [N, K] fp32
+    db = ops.rowsum_bf16(dyT)
+    Wb = W.to(bf16).float()
+    assert _rel(dx, dy.float() @ Wb) < 4e-3
+    assert _rel(dW, dy.float().t() @ x.float()) < 1e-3
+    assert _rel(db, dy.float().sum(0)) < 1e-4
+
+
+def test_embedding_grads(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(12)
+    B, S, D, V = 4, 77, 512, 1000
+    ids = torch.randint(0, V, (B, S), device=cuda, generator=g)
+    ids[:, 0] = 7  # collisions
+    d = torch.randn(B * S, D, device=cuda, generator=g)
+    dtok = torch.zeros(V, D, device=cuda)
+    ops.embed_scatter_add(d, ids.view(-1), dtok)
+    ref = torch.zeros(V, D, device=cuda).index_add_(0, ids.view(-1), d)
+    assert _rel(dtok, ref) < 1e-5
+    assert _rel(ops.colsum_f32(d.view(B, S * D)).view(S, D), d.view(B, S, D).sum(0)) < 1e-5
+    # vision tokens without the LayerNorm
+    Sv, Dv = 50, 768
+    patch = torch.randn(B * (Sv - 1), Dv, device=cuda, generator=g).to(bf16)
+    cls = torch.randn(Dv, device=cuda, generator=g)
+    pos = torch.randn(Sv, Dv, device=cuda, generator=g)
+    e = ops.vision_embed(patch, cls, pos, B, Sv)
+    ref = torch.cat([cls.expand(B, 1, Dv), patch.float().view(B, Sv - 1, Dv)], 1) + pos[None]
+    assert _rel(e, ref.view(B * Sv, Dv)) < 4e-3
+
+
+def test_linear_f32_wgrad(cuda):
+    from vlm_clip_b200 import ops
+
+    g = _gen(13)
+    x = torch.randn(37, 768, device=cuda, generator=g)
+    dy = torch.randn(37, 512, device=cuda, generator=g)
+    assert _rel(ops.linear_f32_wgrad(dy, x), dy.t() @ x) < 1e-5

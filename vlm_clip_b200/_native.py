@@ -53,6 +53,18 @@ PROTOTYPES = {
     "vlmclip_l2norm_rows_bwd": (_i, [_p, _p, _p, _i, _i, _p]),
     "vlmclip_adamw_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vlmclip_gather_rows_bf16_to_f32": (_i, [_p, _i64, _p, _i, _i, _p]),
+    "vlmclip_transpose_to_bf16": (_i, [_p, _i, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    "vlmclip_cast_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
+    "vlmclip_rowsum_bf16": (_i, [_p, _i64, _p, _i, _i, _p]),
+    "vlmclip_colsum_f32": (_i, [_p, _i64, _p, _i, _i64, _p]),
+    "vlmclip_quick_gelu_bf16": (_i, [_p, _p, _i64, _p]),
+    "vlmclip_quick_gelu_bwd_bf16": (_i, [_p, _p, _p, _i64, _p]),
+    "vlmclip_layernorm_bwd_workspace": (_i64, [_i, _i]),
+    "vlmclip_layernorm_bwd": (_i, [_p, _i, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
+    "vlmclip_vision_embed": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "vlmclip_embed_scatter_add": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _p]),
+    "vlmclip_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "vlmclip_linear_f32_wgrad": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p]),
 }
 
 

@@ -436,6 +436,18 @@ linear_f32_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ 
       });
 }
 
+// dW[N,K] = dy[R,N]^T x[R,K]   (weight gradient of a trainable projection: full fine-tune, HF:784-785)
+__global__ void __launch_bounds__(TF_THREADS)
+linear_f32_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t ldx, float* __restrict__ dW,
+                        int R, int N, int K) {
+  const int m0 = blockIdx.x * TF_TILE, n0 = blockIdx.y * TF_TILE;  // m over N (output features), n over K
+  tile_gemm_f32(
+      R, m0, n0, false, false, [&](int m, int r) { return (m < N && r < R) ? dy[(int64_t)r * N + m] : 0.f; },
+      [&](int n, int r) { return (n < K && r < R) ? x[(int64_t)r * ldx + n] : 0.f; },
+      [&](int m, int n, float v) {
+        if (m < N && n < K) dW[(int64_t)m * K + n] = v;
+      });
+}
 int check_adapter_args(const void* x, const float* W1, const float* b1, const float* W2, const float* b2,
                        const float* gamma, const float* beta, int R, int D, int A, int act, int post,
                        int64_t ldx) {
@@ -560,6 +572,15 @@ extern "C" int vlmclip_linear_f32(const float* x, int64_t ldx, const float* W, c
   count_launch(1);
   linear_f32_kernel<<<grid, TF_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, W, b, y, R, N, K);
   return report_cuda(cudaGetLastError(), "linear_f32_kernel launch");
+}
+
+extern "C" int vlmclip_linear_f32_wgrad(const float* dy, const float* x, int64_t ldx, float* dW, int R, int N, int K,
+                                        void* stream) {
+  VLMCLIP_CHECK_ARG(dy && x && dW && R > 0 && N > 0 && K > 0 && ldx >= K, "linear_f32_wgrad: bad arguments");
+  dim3 grid((N + TF_TILE - 1) / TF_TILE, (K + TF_TILE - 1) / TF_TILE);
+  count_launch(1);
+  linear_f32_wgrad_kernel<<<grid, TF_THREADS, 0, (cudaStream_t)stream>>>(dy, x, ldx, dW, R, N, K);
+  return report_cuda(cudaGetLastError(), "linear_f32_wgrad_kernel launch");
 }
 
 extern "C" int vlmclip_linear_f32_dgrad(const float* dy, const float* W, float* dx, int R, int N, int K,

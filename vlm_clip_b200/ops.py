@@ -291,6 +291,155 @@ def gather_rows_f32(x, rows: int, ld: int, D: int):
     return out
 
 
+# ------------------------------------------------------------------------- backbone backward (full fine-tune)
+@_traced
+def transpose_bf16(src, Rpad=None, gather=None, out=None):
+    """out[c, r] = bf16(src[row(r), c]); src [R, C] bf16 or fp32 (row-major, any row stride); out bf16 [C, Rpad] with
+    zero-filled columns [R, Rpad) (Rpad defaults to R rounded up to 8: the K of the GEMM that consumes it).
+    `gather=(group_dst, group_src, group_off)` reads row (r // group_dst) * group_src + group_off + r % group_dst."""
+    _req(src.dim() == 2 and src.stride(1) == 1 and src.dtype in (bf16, f32), "transpose_bf16: src must be bf16/fp32 [R, C]")
+    C = src.shape[1]
+    gd, gs, go = gather if gather is not None else (0, 0, 0)
+    R = src.shape[0] if gather is None else (src.shape[0] // gs) * gd
+    if Rpad is None:
+        Rpad = (R + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((C, Rpad), device=src.device, dtype=bf16)
+    _req(out.dtype == bf16 and out.shape[0] == C and out.shape[1] >= Rpad and out.stride(1) == 1, "transpose_bf16: bad out")
+    N.check(
+        N.load().vlmclip_transpose_to_bf16(N.ptr(src), 1 if src.dtype == f32 else 0, src.stride(0), N.ptr(out), out.stride(0),
+                                           R, Rpad, C, gd, gs, go, N.stream()), "vlmclip_transpose_to_bf16")
+    return out
+
+
+@_traced
+def cast_bf16(src, out=None):
+    _req(src.dtype == f32 and src.is_contiguous(), "cast_bf16: src must be contiguous fp32")
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=bf16)
+    _req(out.dtype == bf16 and out.is_contiguous() and out.numel() == src.numel(), "cast_bf16: bad out")
+    N.check(N.load().vlmclip_cast_f32_to_bf16(N.ptr(src), N.ptr(out), src.numel(), N.stream()), "vlmclip_cast_f32_to_bf16")
+    return out
+
+
+@_traced
+def rowsum_bf16(x):
+    _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "rowsum_bf16: x must be bf16 [R, C]")
+    out = torch.empty((x.shape[0],), device=x.device, dtype=f32)
+    N.check(N.load().vlmclip_rowsum_bf16(N.ptr(x), x.stride(0), N.ptr(out), x.shape[0], x.shape[1], N.stream()),
+            "vlmclip_rowsum_bf16")
+    return out
+
+
+@_traced
+def colsum_f32(x):
+    _req(x.dtype == f32 and x.dim() == 2 and x.stride(1) == 1, "colsum_f32: x must be fp32 [R, C]")
+    out = torch.empty((x.shape[1],), device=x.device, dtype=f32)
+    N.check(N.load().vlmclip_colsum_f32(N.ptr(x), x.stride(0), N.ptr(out), x.shape[0], x.shape[1], N.stream()),
+            "vlmclip_colsum_f32")
+    return out
+
+
+@_traced
+def quick_gelu(a, out=None):
+    _req(a.dtype == bf16 and a.is_contiguous(), "quick_gelu: a must be contiguous bf16")
+    if out is None:
+        out = torch.empty_like(a)
+    N.check(N.load().vlmclip_quick_gelu_bf16(N.ptr(a), N.ptr(out), a.numel(), N.stream()), "vlmclip_quick_gelu_bf16")
+    return out
+
+
+@_traced
+def quick_gelu_bwd(a, dy, out=None):
+    _req(a.dtype == bf16 and dy.dtype == bf16 and a.is_contiguous() and dy.is_contiguous() and a.shape == dy.shape,
+         "quick_gelu_bwd: a, dy must be contiguous bf16 of one shape")
+    if out is None:
+        out = torch.empty_like(a)
+    N.check(N.load().vlmclip_quick_gelu_bwd_bf16(N.ptr(a), N.ptr(dy), N.ptr(out), a.numel(), N.stream()),
+            "vlmclip_quick_gelu_bwd_bf16")
+    return out
+
+
+@_traced
+def layernorm_bwd(dy, x, gamma, eps=1e-5, dres=None, dx_f32=None, dx_bf16=None, param_grads=True):
+    """LayerNorm backward.  dy [M, D] bf16 or fp32, x = the LayerNorm's bf16 input [M, D] (both may be row-strided views);
+    dres / dx_f32 (fp32) and dx_bf16 share one row stride.  Returns (dgamma, dbeta) (or (None, None))."""
+    _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm_bwd: x must be bf16 [M, D]")
+    _req(dy.dtype in (bf16, f32) and dy.shape == x.shape and dy.stride(1) == 1, "layernorm_bwd: dy must match x")
+    M, D = x.shape
+    lddx = 0
+    for t, dt in ((dres, f32), (dx_f32, f32), (dx_bf16, bf16)):
+        if t is not None:
+            _req(t.dtype == dt and t.shape == x.shape and t.stride(1) == 1, "layernorm_bwd: bad dres / dx")
+            _req(lddx in (0, t.stride(0)), "layernorm_bwd: dres, dx_f32 and dx_bf16 must share one row stride")
+            lddx = t.stride(0)
+    lib = N.load()
+    dgamma = dbeta = ws = None
+    if param_grads:
+        dgamma = torch.empty((D,), device=x.device, dtype=f32)
+        dbeta = torch.empty((D,), device=x.device, dtype=f32)
+        ws = torch.empty(lib.vlmclip_layernorm_bwd_workspace(M, D), device=x.device, dtype=f32)
+    N.check(
+        lib.vlmclip_layernorm_bwd(N.ptr(dy), 1 if dy.dtype == f32 else 0, dy.stride(0), N.ptr(x), x.stride(0), N.ptr(gamma),
+                                  N.ptr(dres), N.ptr(dx_f32), N.ptr(dx_bf16), lddx, N.ptr(dgamma), N.ptr(dbeta), N.ptr(ws),
+                                  M, D, float(eps), N.stream()), "vlmclip_layernorm_bwd")
+    return dgamma, dbeta
+
+
+@_traced
+def vision_embed(patch, cls, pos, B: int, S: int, out=None):
+    """Vision tokens without pre_layrnorm: bf16 [B*S, D] (the saved LayerNorm input of the training path)."""
+    D = pos.shape[1]
+    _req(patch.dtype == bf16 and patch.shape == (B * (S - 1), D) and patch.is_contiguous(),
+         "vision_embed: patch must be contiguous bf16 [B*(S-1), D]")
+    if out is None:
+        out = torch.empty((B * S, D), device=pos.device, dtype=bf16)
+    N.check(N.load().vlmclip_vision_embed(N.ptr(patch), N.ptr(cls), N.ptr(pos), N.ptr(out), B, S, D, N.stream()),
+            "vlmclip_vision_embed")
+    return out
+
+
+@_traced
+def embed_scatter_add(d, ids, dtok):
+    """dtok[ids[r]] += d[r]: d fp32 [rows, D], ids int64 [rows], dtok fp32 [V, D] (zeroed by the caller)."""
+    _req(d.dtype == f32 and d.dim() == 2 and d.stride(1) == 1 and dtok.dtype == f32 and dtok.is_contiguous(),
+         "embed_scatter_add: fp32 operands")
+    _req(ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == d.shape[0], "embed_scatter_add: ids")
+    N.check(
+        N.load().vlmclip_embed_scatter_add(N.ptr(d), d.stride(0), N.ptr(ids), N.ptr(dtok), d.shape[0], d.shape[1],
+                                           dtok.shape[0], N.stream()), "vlmclip_embed_scatter_add")
+    return dtok
+
+
+@_traced
+def attention_bwd(qkv, out, dout, B: int, S: int, H: int, causal=False, key_mask=None, scale=None, dqkv=None):
+    for t, w in ((qkv, 3 * H * 64), (out, H * 64), (dout, H * 64)):
+        _req(t.dtype == bf16 and t.shape == (B * S, w) and t.is_contiguous(), "attention_bwd: contiguous bf16 operands")
+    if key_mask is not None:
+        _req(key_mask.dtype == torch.uint8 and key_mask.shape == (B, S) and key_mask.is_contiguous(),
+             "attention_bwd: key_mask must be uint8 [B,S]")
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    N.check(
+        N.load().vlmclip_attention_bwd(N.ptr(qkv), N.ptr(out), N.ptr(dout), N.ptr(dqkv), N.ptr(key_mask), B, S, H,
+                                       1 if causal else 0, float(scale if scale is not None else 64 ** -0.5), N.stream()),
+        "vlmclip_attention_bwd")
+    return dqkv
+
+
+@_traced
+def linear_f32_wgrad(dy, x):
+    """dW[N, K] = dy[R, N]^T x[R, K] (fp32)."""
+    _req(dy.dtype == f32 and dy.is_contiguous() and x.dtype == f32 and x.stride(1) == 1 and dy.shape[0] == x.shape[0],
+         "linear_f32_wgrad: fp32 dy [R, N], x [R, K]")
+    R, Nn = dy.shape
+    K = x.shape[1]
+    dW = torch.empty((Nn, K), device=dy.device, dtype=f32)
+    N.check(N.load().vlmclip_linear_f32_wgrad(N.ptr(dy), N.ptr(x), x.stride(0), N.ptr(dW), R, Nn, K, N.stream()),
+            "vlmclip_linear_f32_wgrad")
+    return dW
+
+
 # --------------------------------------------------------------------------------------------- adapters
 class _AdapterFn(torch.autograd.Function):
     """Fused bottleneck adapter (vlmclip_adapter_fwd / vlmclip_adapter_bwd)."""
