@@ -31,6 +31,7 @@ from . import ops
 from .adapter.clip_adapter import SharedMHSAttentionAdapter, TextAdapter, VisionAdapter
 from .adapter.peclip import TextualAdapter
 from .constants import CLIP_MEAN, CLIP_STD
+from .finetune import TrainableClipTowers, linear_f32_trainable
 from .towers import NativeClipTowers
 
 
@@ -103,6 +104,7 @@ class CLIPWithAdapters(nn.Module):
 
         self._towers = None
         self._towers_key = None
+        self._ft_towers = None
         self._dp_group = None
         self._dp_enabled = False
         # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
@@ -132,15 +134,51 @@ class CLIPWithAdapters(nn.Module):
         p = next(self.clip.parameters())
         if p.device.type != "cuda":
             raise N.NativeError("CLIPWithAdapters runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda')")
-        if torch.is_grad_enabled() and any(q.requires_grad for q in self.clip.parameters()):
-            raise N.NativeError("full fine-tuning (freeze_clip=False) needs the backbone backward kernels, which are "
-                                "not built yet (BASELINE config 5); keep the CLIP weights frozen")
         key = (str(p.device), p.data_ptr(), p._version)
         if self._towers is None or self._towers_key != key:
             self._towers = NativeClipTowers(self.clip, p.device)
             self._towers_key = key
             torch.cuda.current_stream().synchronize()  # packed weights are read from the private tower streams
         return self._towers
+
+    def _full_finetune(self) -> bool:
+        """True when CLIP parameters are trainable (`freeze_clip=False` / `_unfreeze_clip_parameters`, model_m.py:22,
+        72-75; BASELINE config 5): the towers then run from the live fp32 parameters and are differentiated
+        (finetune.TrainableClipTowers) instead of from the packed, LayerNorm-folded frozen copy."""
+        return any(q.requires_grad for q in self.clip.parameters())
+
+    def _finetune_towers(self) -> TrainableClipTowers:
+        p = next(self.clip.parameters())
+        if p.device.type != "cuda":
+            raise N.NativeError("CLIPWithAdapters runs on CUDA only (sm_100a kernels, no CPU fallback): call .to('cuda')")
+        if self._ft_towers is None or self._ft_towers.clip is not self.clip:
+            self._ft_towers = TrainableClipTowers(self.clip)
+        return self._ft_towers
+
+    def _ft_text_features(self, input_ids, attention_mask):
+        ft = self._finetune_towers()
+        tok0 = ft.text_tok0(input_ids, attention_mask)  # final_layer_norm(hidden)[:, 0], fp32 [B, Dt]
+        if self.use_text_adapter:
+            tok0 = self.text_adapter(tok0)
+        if self.use_shared_adapters:
+            table = self.clip.vision_model.embeddings.position_embedding.weight.unsqueeze(0)
+            for shared_adapter in self.shared_adapters:
+                tok0 = shared_adapter(tok0.unsqueeze(1), table).squeeze(1)
+        return linear_f32_trainable(tok0.contiguous(), ft.text_projection)
+
+    def _ft_image_features(self, pixel_values):
+        ft = self._finetune_towers()
+        if pixel_values.dtype == torch.uint8:
+            raise N.NativeError("full fine-tuning takes float pixel_values [B, 3, H, W] (uint8 frames: frozen towers only)")
+        T = None
+        if pixel_values.dim() == 5:
+            B, C, T, H, W = pixel_values.shape
+            pixel_values = pixel_values.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+        cls = ft.vision_cls(pixel_values)  # last_hidden_state[:, 0] (no post_layernorm), fp32 [B, Dv]
+        if self.use_vision_adapter:
+            cls = self.vision_adapter(cls)
+        feats = linear_f32_trainable(cls.contiguous(), ft.visual_projection)
+        return feats if T is None else ops.mean_pool(feats, T)
 
     def refresh_backbone(self):
         """Re-pack the frozen CLIP weights (call after loading new backbone weights in place)."""
@@ -153,6 +191,8 @@ class CLIPWithAdapters(nn.Module):
 
     def get_text_features(self, input_ids, attention_mask):
         """Text features with adapter: fp32 [B, P] (reference: model_m.py:77-105)."""
+        if self._full_finetune():
+            return self._ft_text_features(input_ids, attention_mask)
         bb = self._backbone()
         input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
         hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
@@ -183,6 +223,8 @@ class CLIPWithAdapters(nn.Module):
 
         `pixel_values`: float [B, 3, H, W] as in the reference, or (extension) decoded uint8 frames [B, Hs, Ws, 3], which
         are resized / scaled / normalised on the GPU (`self.pixel_mean`, `self.pixel_std`, `self.frames_bgr`)."""
+        if self._full_finetune():
+            return self._ft_image_features(pixel_values)
         bb = self._backbone()
         hidden, n, seq = self._vision_hidden(bb, pixel_values)
         return self._image_head(bb, hidden, n, seq)
@@ -193,6 +235,8 @@ class CLIPWithAdapters(nn.Module):
         `process_video` outputs, process_video.py:29) or decoded uint8 frames [B, T, Hs, Ws, 3]."""
         if clips.dim() != 5:
             raise ValueError("clips must be [B, 3, T, H, W] float or [B, T, Hs, Ws, 3] uint8")
+        if self._full_finetune():
+            return self._ft_image_features(clips)
         T = clips.shape[1] if clips.dtype == torch.uint8 else clips.shape[2]
         bb = self._backbone()
         hidden, n, seq = self._vision_hidden(bb, clips)
@@ -223,7 +267,7 @@ class CLIPWithAdapters(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True, *, inputs_ready=None):
         """Same contract as the reference (model_m.py:127-176): 5-key dict with the loss, 2-key dict without."""
         both = input_ids is not None and attention_mask is not None and pixel_values is not None
-        if both and self.overlap_towers and pixel_values.is_cuda:
+        if both and self.overlap_towers and pixel_values.is_cuda and not self._full_finetune():
             text_features, image_features = self._both_towers(input_ids, attention_mask, pixel_values, inputs_ready)
         else:
             if input_ids is not None and attention_mask is not None:
@@ -238,6 +282,8 @@ class CLIPWithAdapters(nn.Module):
 
         if return_loss and text_features is not None and image_features is not None:
             scale = self._logit_scale_exp()
+            ls = self.clip.logit_scale
+            ls_param = ls if (ls.requires_grad and torch.is_grad_enabled()) else None
             txt_all = img_all = None
             row0 = 0
             if self._dp_enabled:
@@ -245,7 +291,8 @@ class CLIPWithAdapters(nn.Module):
 
                 if world(self._dp_group)[0] > 1:
                     txt_all, img_all, row0 = gather_features(text_features, image_features, self._dp_group)
-            loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0)
+            loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0,
+                                                            logit_scale=ls_param)
             return {
                 "loss": loss,
                 "text_features": t_n,
@@ -300,6 +347,10 @@ class CLIPWithAdapters(nn.Module):
     def _logit_scale_exp(self) -> float:
         # logit_scale is a frozen scalar parameter: cache exp() on the host, re-read only when it is modified
         ls = self.clip.logit_scale
+        if ls.requires_grad:
+            # trainable scale (full fine-tune): the fused optimiser updates it in place behind autograd's version
+            # counter, so it is read back every step (one 4-byte D2H copy against a ~100 ms step)
+            return float(ls.detach().exp().item())
         key = (ls.data_ptr(), ls._version)
         if getattr(self, "_ls_key", None) != key:
             self._ls_val = float(ls.detach().exp().item())

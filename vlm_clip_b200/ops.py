@@ -604,7 +604,7 @@ class _ClipLossFn(torch.autograd.Function):
     """Symmetric InfoNCE over the (global) batch; gradients for rows [row0, row0 + nloc) only."""
 
     @staticmethod
-    def forward(ctx, txt_local, img_local, txt_all, img_all, scale_exp, row0, want_logits):
+    def forward(ctx, txt_local, img_local, txt_all, img_all, scale_exp, row0, want_logits, logit_scale=None):
         Ng, P = txt_all.shape
         nloc = txt_local.shape[0]
         dev = txt_all.device
@@ -616,11 +616,15 @@ class _ClipLossFn(torch.autograd.Function):
         d_txt = torch.empty((nloc, P), device=dev, dtype=f32)
         d_img = torch.empty((nloc, P), device=dev, dtype=f32)
         ws = torch.empty(lib.vlmclip_clip_loss_workspace(Ng, P), device=dev, dtype=f32)
+        # trainable logit_scale (full fine-tune): the kernel also returns dL/d(log scale) for this rank's rows
+        d_ls = torch.empty((1,), device=dev, dtype=f32) if logit_scale is not None else None
         N.check(
             lib.vlmclip_clip_loss(N.ptr(txt_all), N.ptr(img_all), float(scale_exp), N.ptr(txt_n), N.ptr(img_n),
-                                  N.ptr(logits), N.ptr(loss), N.ptr(d_txt), N.ptr(d_img), None, N.ptr(ws), Ng, P,
+                                  N.ptr(logits), N.ptr(loss), N.ptr(d_txt), N.ptr(d_img), N.ptr(d_ls), N.ptr(ws), Ng, P,
                                   int(row0), nloc, N.stream()), "vlmclip_clip_loss")
         ctx.save_for_backward(d_txt, d_img)
+        ctx.d_ls = d_ls
+        ctx.ls_shape = tuple(logit_scale.shape) if logit_scale is not None else None
         ctx.mark_non_differentiable(txt_n, img_n)
         if logits is not None:
             ctx.mark_non_differentiable(logits)
@@ -630,20 +634,23 @@ class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, *_):
         d_txt, d_img = ctx.saved_tensors
-        return d_txt * dloss, d_img * dloss, None, None, None, None, None
+        d_ls = (ctx.d_ls * dloss).reshape(ctx.ls_shape) if ctx.d_ls is not None else None
+        return d_txt * dloss, d_img * dloss, None, None, None, None, None, d_ls
 
 
 def clip_loss(txt_local, img_local, logit_scale_exp: float, txt_all=None, img_all=None, row0: int = 0,
-              want_logits: bool = True):
+              want_logits: bool = True, logit_scale=None):
     """Returns (loss, txt_normalised_all, img_normalised_all, logits_per_text_all).
 
     txt_all / img_all: the all-gathered un-normalised features under data parallelism (default: the local ones).
+    logit_scale: the (log) scale PARAMETER when it is trainable (full fine-tune); it then receives its gradient.
     """
     if txt_all is None:
         txt_all, img_all, row0 = txt_local.detach(), img_local.detach(), 0
     for t in (txt_local, img_local, txt_all, img_all):
         _req(t.dtype == f32 and t.dim() == 2 and t.is_contiguous(), "clip_loss: features must be contiguous fp32 [N, P]")
-    return _ClipLossFn.apply(txt_local, img_local, txt_all, img_all, float(logit_scale_exp), int(row0), want_logits)
+    return _ClipLossFn.apply(txt_local, img_local, txt_all, img_all, float(logit_scale_exp), int(row0), want_logits,
+                             logit_scale)
 
 
 class _ClassHeadFn(torch.autograd.Function):
@@ -712,20 +719,25 @@ class FusedAdamW:
         self.params = [p for p in params]
         _req(len(self.params) > 0, "FusedAdamW: empty parameter list")
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary of the arena (the kernels read weights / biases with 16-byte
+        # vector loads; a scalar such as logit_scale would otherwise shift everything behind it).  The gaps hold
+        # zero parameters with zero gradients: they add nothing to the gradient norm and stay zero under AdamW.
+        self.offsets = []
+        n = 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4
         self.n = n
-        self.flat = torch.empty(n, device=dev, dtype=f32)
+        self.flat = torch.zeros(n, device=dev, dtype=f32)
         self.grad = torch.zeros(n, device=dev, dtype=f32)
         self.exp_avg = torch.zeros(n, device=dev, dtype=f32)
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=f32)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             _req(p.dtype == f32 and p.device == dev, "FusedAdamW: parameters must be fp32 on one device")
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
         self.lr = torch.full((1,), float(lr), device=dev, dtype=f32)
         self._lr_on_device = float(lr)
         self.betas, self.eps, self.weight_decay, self.max_grad_norm = betas, eps, weight_decay, max_grad_norm
@@ -737,12 +749,10 @@ class FusedAdamW:
 
     def zero_grad(self, set_to_none: bool = False):
         self.grad.zero_()
-        off = 0
-        for p in self.params:  # keep .grad pointing into the arena even if someone set it to None
+        for p, off in zip(self.params, self.offsets):  # keep .grad pointing into the arena even if someone set it to None
             k = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
                 p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
 
     def set_lr(self, lr: float):
         self.param_groups[0]["lr"] = float(lr)

@@ -51,6 +51,7 @@ class CLIPAdapterTrainer:
         max_grad_norm=1.0,
         output_dir="./clip_adapter_checkpoints",
         log_every=10,
+        trainable="adapters",
     ):
         self.model = model
         self.train_dataloader = train_dataloader
@@ -63,9 +64,21 @@ class CLIPAdapterTrainer:
         self.log_every = max(1, int(log_every))
         os.makedirs(output_dir, exist_ok=True)
 
+        # `trainable` is an extension (BASELINE config 5): "adapters" is the reference's name filter (trainer.py:39-43);
+        # "all" optimises every parameter that requires grad (full fine-tune after `_unfreeze_clip_parameters()`),
+        # minus the ones the model never reads: torch.optim skips parameters whose .grad stays None, the fused arena
+        # optimiser has no such notion and would still weight-decay them.
+        if trainable not in ("adapters", "all"):
+            raise ValueError(f"trainable must be 'adapters' or 'all', got {trainable!r}")
         self.trainable_params = []
+        skip = set()
+        if trainable == "all" and hasattr(model, "_finetune_towers") and model._full_finetune():
+            skip = {id(q) for q in model._finetune_towers().unused_parameters()}
         for name, param in model.named_parameters():
-            if "adapter" in name or "shared_adapters" in name:
+            if trainable == "all":
+                if param.requires_grad and id(param) not in skip:
+                    self.trainable_params.append(param)
+            elif "adapter" in name or "shared_adapters" in name:
                 self.trainable_params.append(param)
         if not self.trainable_params:
             raise ValueError("optimizer got an empty parameter list")  # what torch.optim.AdamW raises
