@@ -272,9 +272,12 @@ int vlmclip_vision_embed(const void* patch, const float* cls, const float* pos, 
 int vlmclip_embed_scatter_add(const float* d, int64_t ldd, const int64_t* ids, float* dtok, int64_t rows, int D, int V,
                               void* stream);
 /* Backward of vlmclip_attention_fwd: dqkv [B*S, 3D] (bf16, WRITTEN) from qkv, out = forward output [B*S, D] and its
- * gradient dout.  Probabilities are recomputed (nothing else is kept from the forward).  S <= 288, head_dim 64. */
-int vlmclip_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask, int B,
-                          int S, int H, int causal, float scale, void* stream);
+ * gradient dout.  Probabilities are recomputed (nothing else is kept from the forward).  head_dim 64.
+ *   workspace: vlmclip_attention_bwd_workspace(B, S, H) floats (row log-sum-exp and dO.O) -> tensor-core kernels
+ *   (mma.sync bf16, S <= 512); NULL -> the fp32 SIMT reference kernel (S <= 288), kept for the parity tests. */
+int64_t vlmclip_attention_bwd_workspace(int B, int S, int H);
+int vlmclip_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask,
+                          float* workspace, int B, int S, int H, int causal, float scale, void* stream);
 /* dW[N,K] = dy[R,N]^T x[R,K] (fp32): weight gradient of vlmclip_linear_f32 when the projection is trainable */
 int vlmclip_linear_f32_wgrad(const float* dy, const float* x, int64_t ldx, float* dW, int R, int N, int K, void* stream);
 

@@ -63,7 +63,8 @@ PROTOTYPES = {
     "vlmclip_layernorm_bwd": (_i, [_p, _i, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_vision_embed": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "vlmclip_embed_scatter_add": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _p]),
-    "vlmclip_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "vlmclip_attention_bwd_workspace": (_i64, [_i, _i, _i]),
+    "vlmclip_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "vlmclip_linear_f32_wgrad": (_i, [_p, _p, _i64, _p, _i, _i, _i, _p]),
 }
 

@@ -6,8 +6,8 @@
 // saved activations (nothing but qkv and O is kept from the forward).  Phase 1: one warp per query row (scores,
 // soft-max statistics, dQ); phase 2: one warp per key row (dK, dV) with the row statistics of phase 1.
 // 7 x 2 S^2 64 FLOPs per head on the FMA pipe: ~16 TFLOP/s at best, i.e. several ms per ViT-B/16 layer at batch 256.
-// The tensor-core version (tcgen05, S/P/dP in TMEM as in attention_pp.cu) is the planned replacement; this kernel
-// is what the parity tests of the full fine-tune path are pinned on.
+// The product path is the tensor-core pair of kernels in attention_bwd_mma.cu (selected by passing a workspace);
+// this kernel remains as an independent implementation the parity tests compare it with.
 #include "../../include/vlmclip.h"
 #include "common.cuh"
 
@@ -188,15 +188,30 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 
 using namespace vlmclip;
 
+namespace vlmclip {
+int64_t attention_bwd_mma_workspace(int B, int S, int H);
+int attention_bwd_mma(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask,
+                      float* workspace, int B, int S, int H, int causal, float scale, cudaStream_t stream);
+}  // namespace vlmclip
+
+extern "C" int64_t vlmclip_attention_bwd_workspace(int B, int S, int H) {
+  return vlmclip::attention_bwd_mma_workspace(B, S, H);
+}
+
 extern "C" int vlmclip_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv,
-                                     const uint8_t* key_mask, int B, int S, int H, int causal, float scale,
-                                     void* stream) {
+                                     const uint8_t* key_mask, float* workspace, int B, int S, int H, int causal,
+                                     float scale, void* stream) {
   VLMCLIP_CHECK_ARG(qkv && out && dout && dqkv, "attention_bwd: null pointer");
-  VLMCLIP_CHECK_ARG(B > 0 && H > 0 && S > 0 && S <= 32 * AB_MAX_JT, "attention_bwd: S=%d must be in [1, %d]", S,
-                    32 * AB_MAX_JT);
+  VLMCLIP_CHECK_ARG(B > 0 && H > 0 && S > 0, "attention_bwd: bad dims B=%d S=%d H=%d", B, S, H);
   VLMCLIP_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)dout % 16 == 0 &&
                         (uintptr_t)dqkv % 16 == 0,
                     "attention_bwd: pointers must be 16-byte aligned");
+  if (workspace != nullptr) {  // tensor-core kernels (attention_bwd_mma.cu)
+    VLMCLIP_CHECK_ARG(S <= 512, "attention_bwd: S=%d must be <= 512", S);
+    return attention_bwd_mma(qkv, out, dout, dqkv, key_mask, workspace, B, S, H, causal, scale, (cudaStream_t)stream);
+  }
+  // no workspace: the fp32 SIMT kernel of this file (independent implementation, kept for the parity tests)
+  VLMCLIP_CHECK_ARG(S <= 32 * AB_MAX_JT, "attention_bwd (SIMT): S=%d must be <= %d", S, 32 * AB_MAX_JT);
   const int Spad = (S + 31) / 32 * 32;
   const size_t smem = (size_t)4 * S * AB_LD * 2 + (size_t)(2 + 2 * AB_WARPS) * Spad * 4 + Spad;
   static bool attr_set = false;  // benign race: the attribute is idempotent

@@ -412,7 +412,9 @@ def embed_scatter_add(d, ids, dtok):
 
 
 @_traced
-def attention_bwd(qkv, out, dout, B: int, S: int, H: int, causal=False, key_mask=None, scale=None, dqkv=None):
+def attention_bwd(qkv, out, dout, B: int, S: int, H: int, causal=False, key_mask=None, scale=None, dqkv=None,
+                  simt: bool = False):
+    """dqkv of ops.attention.  `simt=True` selects the fp32 SIMT reference kernel instead of the tensor-core pair."""
     for t, w in ((qkv, 3 * H * 64), (out, H * 64), (dout, H * 64)):
         _req(t.dtype == bf16 and t.shape == (B * S, w) and t.is_contiguous(), "attention_bwd: contiguous bf16 operands")
     if key_mask is not None:
@@ -420,9 +422,11 @@ def attention_bwd(qkv, out, dout, B: int, S: int, H: int, causal=False, key_mask
              "attention_bwd: key_mask must be uint8 [B,S]")
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
+    lib = N.load()
+    ws = None if simt else torch.empty(lib.vlmclip_attention_bwd_workspace(B, S, H), device=qkv.device, dtype=f32)
     N.check(
-        N.load().vlmclip_attention_bwd(N.ptr(qkv), N.ptr(out), N.ptr(dout), N.ptr(dqkv), N.ptr(key_mask), B, S, H,
-                                       1 if causal else 0, float(scale if scale is not None else 64 ** -0.5), N.stream()),
+        lib.vlmclip_attention_bwd(N.ptr(qkv), N.ptr(out), N.ptr(dout), N.ptr(dqkv), N.ptr(key_mask), N.ptr(ws), B, S, H,
+                                  1 if causal else 0, float(scale if scale is not None else 64 ** -0.5), N.stream()),
         "vlmclip_attention_bwd")
     return dqkv
 
