@@ -20,7 +20,9 @@ def _gen(seed):
     return torch.Generator(device="cuda").manual_seed(seed)
 
 
-@pytest.mark.parametrize("R,C,src_f32", [(50, 72, False), (197 * 3, 768, False), (512, 2048, True), (33, 40, True)])
+@pytest.mark.parametrize("R,C,src_f32", [(50, 72, False), (197 * 3, 768, False), (512, 2048, True), (33, 40, True),
+                                         (20, 36, False), (70, 12, True),   # C % 8 != 0: the 32 x 32 scalar kernel
+                                         (1000, 3072, False)])
 def test_transpose_pad(cuda, R, C, src_f32):
     from vlm_clip_b200 import ops
 

@@ -76,6 +76,52 @@ transpose_to_bf16_kernel(const T* __restrict__ src, int64_t lds, __nv_bfloat16* 
   }
 }
 
+// Fast path (C % 8 == 0, 16-byte aligned rows): 64 x 64 tiles, every global access a 16-byte vector, 128 contiguous
+// bytes per 8 lanes on both sides.  The tile sits in shared memory as 64 rows x 8 chunks of 16 B with the chunk
+// index XOR-swizzled by (row / 8), so that the column gathers of the write phase (8 rows r = 8k + i of one column,
+// k = lane % 8) fall into 8 different 4-bank groups.
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose64_to_bf16_kernel(const T* __restrict__ src, int64_t lds, __nv_bfloat16* __restrict__ dst, int64_t ldd, int R,
+                           int Rpad, int C, int group_dst, int group_src, int group_off) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * 64];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int q = threadIdx.x + 256 * p;
+    const int r = q >> 3, ch = q & 7;
+    const int gr = r0 + r, gc = c0 + ch * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gr < R && gc < C) {
+      const int64_t sr = group_dst > 0 ? (int64_t)(gr / group_dst) * group_src + group_off + (gr % group_dst) : gr;
+      if (sizeof(T) == 4) {
+        float f[8];
+        load8_f32(reinterpret_cast<const float*>(src) + sr * lds + gc, f);
+        v = pack8(f);
+      } else {
+        v = ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(src) + sr * lds + gc);
+      }
+    }
+    *reinterpret_cast<uint4*>(tile + r * 64 + ((ch ^ (r >> 3)) << 3)) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int q = threadIdx.x + 256 * p;
+    const int c = q >> 3, k = q & 7;
+    if (c0 + c < C && r0 + 8 * k < Rpad) {
+      const int pc = (((c >> 3) ^ k) << 3) + (c & 7);  // swizzled column of rows 8k .. 8k+7
+      const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile) + (8 * k) * 64 + pc;
+      uint4 o;
+      o.x = (uint32_t)t16[0] | ((uint32_t)t16[64] << 16);
+      o.y = (uint32_t)t16[128] | ((uint32_t)t16[192] << 16);
+      o.z = (uint32_t)t16[256] | ((uint32_t)t16[320] << 16);
+      o.w = (uint32_t)t16[384] | ((uint32_t)t16[448] << 16);
+      st_v4(dst + (int64_t)(c0 + c) * ldd + r0 + 8 * k, o);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n, int vec_ok) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -366,9 +412,21 @@ extern "C" int vlmclip_transpose_to_bf16(const void* src, int src_f32, int64_t l
                     (long long)ldd, (long long)lds, C);
   VLMCLIP_CHECK_ARG(group_dst == 0 || (group_dst > 0 && group_src >= group_dst + group_off && group_off >= 0),
                     "transpose: bad row gather (%d, %d, %d)", group_dst, group_src, group_off);
+  count_launch(1);
+  const int esz = src_f32 ? 4 : 2;
+  if (C % 8 == 0 && Rpad % 8 == 0 && ldd % 8 == 0 && (lds * esz) % 16 == 0 && (uintptr_t)src % 16 == 0 &&
+      (uintptr_t)dst % 16 == 0 && (C + 63) / 64 <= 65535) {
+    dim3 grid64((Rpad + 63) / 64, (C + 63) / 64);
+    if (src_f32)
+      transpose64_to_bf16_kernel<float><<<grid64, 256, 0, (cudaStream_t)stream>>>(
+          (const float*)src, lds, (__nv_bfloat16*)dst, ldd, R, Rpad, C, group_dst, group_src, group_off);
+    else
+      transpose64_to_bf16_kernel<__nv_bfloat16><<<grid64, 256, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, R, Rpad, C, group_dst, group_src, group_off);
+    return report_cuda(cudaGetLastError(), "transpose64_to_bf16_kernel launch");
+  }
   dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
   VLMCLIP_CHECK_ARG(grid.y <= 65535, "transpose: C=%d too large", C);
-  count_launch(1);
   if (src_f32)
     transpose_to_bf16_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, lds, (__nv_bfloat16*)dst,
                                                                             ldd, R, Rpad, C, group_dst, group_src, group_off);
