@@ -345,6 +345,8 @@ def run_native_arm(args):
                      "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms_step,
                      "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a step)"},
     }
+    if world == 1 and not args.no_full_finetune:
+        line["full_finetune_variant"] = _full_finetune_leg(dev, fl, peak_tf)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_reference_step_rate(steps=3, warmup=1)
         line["cpu_baseline"] = base
@@ -352,6 +354,53 @@ def run_native_arm(args):
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _full_finetune_leg(dev, fl, peak_tf, steps: int = 5):
+    """BASELINE config 5 beside the headline: the same Track-M step with the adapters disabled and EVERY CLIP parameter
+    trainable (`freeze_clip=False`): towers forward from the live fp32 weights, hand-written backward through both
+    towers (dgrad / wgrad on the tcgen05 GEMM, tensor-core attention backward), clip + AdamW over 151 M parameters.
+    Its own model instance; a failure here is reported in the record and never touches the headline numbers."""
+    import torch
+
+    from oracle import clip_oracle as O
+    from vlm_clip_b200 import _native as N
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    try:
+        clip = O.build_hf_clip(MODEL, seed=0).to(dev)
+        model = CLIPWithAdapters(clip=clip, freeze_clip=False, use_text_adapter=False, use_vision_adapter=False,
+                                 use_shared_adapters=False).to(dev)
+        model.train()
+        g = torch.Generator().manual_seed(7)
+        ids = torch.randint(3, 49406, (BATCH, 77), generator=g)
+        ids[:, 0], ids[:, -1] = 49406, 49407
+        batch = {"input_ids": ids.to(dev), "attention_mask": torch.ones(BATCH, 77, dtype=torch.int64, device=dev),
+                 "pixel_values": torch.randn(BATCH, 3, 224, 224, generator=g).to(dev)}
+        tr = CLIPAdapterTrainer(model, [batch], learning_rate=1e-7, output_dir="/tmp/vlmclip_bench_ft", trainable="all")
+        for _ in range(3):
+            tr.training_step(batch)
+        torch.cuda.synchronize()
+        n0 = N.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = tr.training_step(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tflop = 3.0 * fl["pair"] * BATCH / 1e12  # forward + input gradients + weight gradients
+        return {"what": "BASELINE config 5: full fine-tune, adapters disabled, all CLIP parameters trainable "
+                        "(CLIPWithAdapters(freeze_clip=False), trainer(trainable='all')); same batch of 256 pairs",
+                "value": BATCH / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "trainable_parameters": sum(p.numel() for p in tr.trainable_params),
+                "algorithmic_tflop_per_step": tflop, "step_tflops": tflop / (ms / 1e3),
+                "step_frac_of_bf16_sustained_peak": tflop / (ms / 1e3) / peak_tf,
+                "gpu_launches_per_step": int((N.launch_count() - n0) / steps), "final_loss": float(loss.item()),
+                "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    except Exception as e:  # never let the comparison config break the headline line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def _cls_only_skipped_flops(model_name: str) -> float:
@@ -385,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-finetune", action="store_true", help="skip the config-5 (full fine-tune) comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
