@@ -35,6 +35,7 @@ os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
 
 MODEL = "openai/clip-vit-base-patch16"
 BATCH = 256
+ADAPTER_KIND = "clip_adapter"
 METRIC = "adapter fine-tune images/sec (ViT-B/16, bf16)"
 UNIT = "images/s"
 
@@ -184,7 +185,7 @@ def run_native_arm(args):
 
     clip = O.build_hf_clip(MODEL, seed=0).to(dev)
     torch.manual_seed(1)
-    model = CLIPWithAdapters(clip=clip, use_shared_adapters=False).to(dev)
+    model = CLIPWithAdapters(clip=clip, use_shared_adapters=False, adapter_kind=ADAPTER_KIND).to(dev)
     model.train()
     trainer = CLIPAdapterTrainer(model, train_dataloader=[None], output_dir="/tmp/vlmclip_bench_ckpt")
 
@@ -318,7 +319,7 @@ def run_native_arm(args):
             "workload": WORKLOAD,
             "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
             "init": "random (seed 0), no checkpoints offline",
-            "l2": "3 rotating input batches; 154 MB pixel batch and >1 GB of activations per step exceed the 126 MB L2",
+            "l2": f"3 rotating input batches; {BATCH * 3 * 224 * 224 * 4 / 1e6:.0f} MB pixel batch and >1 GB of activations per step exceed the 126 MB L2",
             "algorithmic_tflop_per_step_per_gpu": step_tf,
             "step_tflops_per_gpu": step_tf / (ms_step / 1e3),
             "step_frac_of_bf16_sustained_peak": step_tf / (ms_step / 1e3) / peak_tf,
@@ -435,7 +436,18 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-finetune", action="store_true", help="skip the config-5 (full fine-tune) comparison leg")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 (default, the headline): ViT-B/16 + bottleneck adapters, 256 pairs per GPU.  cfg3 (BASELINE "
+                         "configs[2], not a headline line): ViT-L/14 + PE-CLIP adapters, 512 pairs per GPU = global batch 4096 "
+                         "on 8 GPUs, global contrastive loss over the all-gathered embeddings")
     args = ap.parse_args()
+    if args.workload == "cfg3":
+        global MODEL, BATCH, METRIC, WORKLOAD, ADAPTER_KIND
+        MODEL, BATCH, ADAPTER_KIND = "openai/clip-vit-large-patch14", 512, "peclip"
+        METRIC = "adapter fine-tune images/sec (ViT-L/14 + PE-CLIP adapters, bf16)"
+        WORKLOAD = ("CLIP ViT-L/14 + PE-CLIP adapters (A=256), frozen backbone, Track-M train step with the global contrastive "
+                    "loss over all-gathered embeddings (BASELINE config 3)")
+        args.no_full_finetune = True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -133,7 +133,8 @@ __device__ __forceinline__ void stage_two(__nv_bfloat16* s0, __nv_bfloat16* s1, 
 }
 
 // ------------------------------------------------------------------------------------------------------ dQ
-__global__ void __launch_bounds__(256)
+// 144 registers: two CTAs of 7 warps per SM (154 / 194 registers left one CTA = 7 warps per SM: ncu "warps active" 10 %)
+__global__ void __maxnreg__(144)
 attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                         const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                         const uint8_t* __restrict__ key_mask, float* __restrict__ ws_lse, float* __restrict__ ws_d, int S,
@@ -280,7 +281,7 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------------------ dK, dV
-__global__ void __launch_bounds__(256)
+__global__ void __maxnreg__(144)
 attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                          __nv_bfloat16* __restrict__ dqkv, const uint8_t* __restrict__ key_mask,
                          const float* __restrict__ ws_lse, const float* __restrict__ ws_d, int S, int H, int causal,
@@ -320,10 +321,6 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
     kv_b = kv_b && key_mask[(int64_t)b * S + row_b] != 0;
   }
 
-  uint32_t kf[4][4], vf[4][4];
-  load_a_frag(kf, base + D, ld, row_a, row_b, S, tq);
-  load_a_frag(vf, base + 2 * D, ld, row_a, row_b, S, tq);
-
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -334,8 +331,16 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
   for (int i0 = causal ? j0 : 0; i0 < S16; i0 += 64) {  // causal: queries before the warp's first key see none of them
     const int n16 = min(4, (S16 - i0) >> 4);
     float st[8][4], dpt[8][4];  // S^T and dP^T tiles: rows = keys, columns = queries
-    block_a_bt(st, kf, sQ, i0, n16, lane);
-    block_a_bt(dpt, vf, sG, i0, n16, lane);
+    {  // the warp's K / V fragments are re-read (L1 hits) per block instead of living in 32 registers across the loop
+      uint32_t kf[4][4];
+      load_a_frag(kf, base + D, ld, row_a, row_b, S, tq);
+      block_a_bt(st, kf, sQ, i0, n16, lane);
+    }
+    {
+      uint32_t vf[4][4];
+      load_a_frag(vf, base + 2 * D, ld, row_a, row_b, S, tq);
+      block_a_bt(dpt, vf, sG, i0, n16, lane);
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if ((nt >> 1) < n16) {
@@ -383,7 +388,7 @@ int64_t attention_bwd_mma_workspace(int B, int S, int H) {
 int attention_bwd_mma(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask,
                       float* workspace, int B, int S, int H, int causal, float scale, cudaStream_t stream) {
   const int nblocks = (S + 15) / 16;
-  const int groups = (nblocks + 7) / 8;
+  const int groups = (nblocks + 6) / 7;  // at most 7 warps per CTA: two CTAs fit the register file at 144 registers
   const int qw = (nblocks + groups - 1) / groups;
   const int Spad = nblocks * 16;
   float* ws_lse = workspace;
