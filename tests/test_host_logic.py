@@ -159,3 +159,35 @@ def test_track_tv_modules_construct(tiny_clip):
     assert [n for n, _ in v.named_children()][:4] == ["model", "visual_adapter", "text_adapter", "context_adapter"]
     assert len(v.get_trainable_parameters()) == 12  # model_v.py:355-360
     assert v.visual_adapter.fc1.out_features == 192  # config.py:15
+
+
+def test_full_finetune_host_logic(tmp_path):
+    """Config 5 (freeze_clip=False): mode detection, parameter selection of trainer(trainable=...), no CPU fallback."""
+    from vlm_clip_b200 import _native as N
+    from vlm_clip_b200.finetune import _LAYER_PARAMS, track_m_unused_parameters
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    clip = O.build_hf_clip(B32, seed=0, vision_layers=1, text_layers=1)
+    m = CLIPWithAdapters(clip=clip, freeze_clip=True, use_shared_adapters=False)
+    assert not m._full_finetune()
+    m._unfreeze_clip_parameters()  # model_m.py:72-75
+    assert m._full_finetune()
+    # the reference's trainer filters by name whatever requires grad (trainer.py:39-43): still the 12 adapter tensors
+    assert len(CLIPAdapterTrainer(m, [None], output_dir=str(tmp_path / "a")).trainable_params) == 12
+    tr = CLIPAdapterTrainer(m, [None], output_dir=str(tmp_path / "b"), trainable="all")
+    unused = {id(p) for p in track_m_unused_parameters(clip)}
+    assert len(unused) == 2
+    want = [p for p in m.parameters() if p.requires_grad and id(p) not in unused]
+    assert [id(p) for p in tr.trainable_params] == [id(p) for p in want]
+    assert sum(p.numel() for p in tr.trainable_params) == sum(p.numel() for p in m.parameters()) - 2 * 768
+    with pytest.raises(ValueError, match="trainable"):
+        CLIPAdapterTrainer(m, [None], output_dir=str(tmp_path / "c"), trainable="backbone")
+    # every parameter of an encoder layer is covered by the hand-written backward
+    names = {k.split("encoder.layers.0.")[1] for k, _ in clip.named_parameters() if "vision_model.encoder.layers.0." in k}
+    assert names == set(_LAYER_PARAMS)
+    pix, ids, mask = O.synthetic_batch(2)
+    with pytest.raises(N.NativeError):  # CPU model: the fine-tune towers refuse, they do not fall back to HF
+        m(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    m._freeze_clip_parameters()
+    assert not m._full_finetune()

@@ -224,6 +224,13 @@ def linear_f32_trainable(x, W):
     return _LinearF32TrainFn.apply(x, W)
 
 
+def track_m_unused_parameters(clip):
+    """CLIP parameters Track M never reads (no gradient; torch.optim skips them, and so must a fused optimiser):
+    vision post_layernorm (model_m.py:110-122 takes last_hidden_state, HF:684-686 applies it to the pooler only)."""
+    named = dict(clip.named_parameters())
+    return [named["vision_model.post_layernorm.weight"], named["vision_model.post_layernorm.bias"]]
+
+
 class TrainableClipTowers:
     """Both towers executed from the live parameters of `clip`, differentiable w.r.t. every one of them."""
 
@@ -264,10 +271,7 @@ class TrainableClipTowers:
         self.text_projection = named["text_projection.weight"]
 
     def unused_parameters(self):
-        """CLIP parameters Track M never reads (no gradient; torch.optim skips them, and so must a fused optimiser):
-        vision post_layernorm (model_m.py:110-122 takes last_hidden_state, HF:684-686 applies it to the pooler only)."""
-        named = dict(self.clip.named_parameters())
-        return [named["vision_model.post_layernorm.weight"], named["vision_model.post_layernorm.bias"]]
+        return track_m_unused_parameters(self.clip)
 
     def vision_cls(self, pixel_values: torch.Tensor) -> torch.Tensor:
         if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:

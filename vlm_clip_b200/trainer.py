@@ -72,8 +72,10 @@ class CLIPAdapterTrainer:
             raise ValueError(f"trainable must be 'adapters' or 'all', got {trainable!r}")
         self.trainable_params = []
         skip = set()
-        if trainable == "all" and hasattr(model, "_finetune_towers") and model._full_finetune():
-            skip = {id(q) for q in model._finetune_towers().unused_parameters()}
+        if trainable == "all" and hasattr(model, "_full_finetune") and model._full_finetune():
+            from .finetune import track_m_unused_parameters
+
+            skip = {id(q) for q in track_m_unused_parameters(model.clip)}
         for name, param in model.named_parameters():
             if trainable == "all":
                 if param.requires_grad and id(param) not in skip:
