@@ -281,6 +281,32 @@ int vlmclip_attention_bwd(const void* qkv, const void* out, const void* dout, vo
 /* dW[N,K] = dy[R,N]^T x[R,K] (fp32): weight gradient of vlmclip_linear_f32 when the projection is trainable */
 int vlmclip_linear_f32_wgrad(const float* dy, const float* x, int64_t ldx, float* dW, int R, int N, int K, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Trainable SharedMHSAttentionAdapter (adapter/clip_adapter.py:69-128 + autograd), fp32 rows: the pieces that the
+ * fp32 linear kernels above do not cover.  Track M evaluates the adapter on token 0 of every caption against the
+ * projected vision position table (model_m.py:93-102): B query rows, one [S, D] key/value table for the batch.
+ * --------------------------------------------------------------------------------------------------------- */
+/* y = LN(x) on fp32 rows (x row stride ldx, y contiguous [M, D]); stats [M][2] = (mean, rstd) kept for the backward */
+int vlmclip_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y, float* stats,
+                          int M, int D, float eps, void* stream);
+/* dx = LN'(dy) (+ dres) [M, D] (optional), dgamma / dbeta [D] (optional, WRITTEN) */
+int vlmclip_layernorm_f32_bwd(const float* dy, const float* x, int64_t ldx, const float* stats, const float* gamma,
+                              const float* dres, float* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+/* nn.GELU() (exact erf) on fp32 and its backward da = dy * gelu'(a) */
+int vlmclip_gelu_f32(const float* a, float* y, int64_t n, void* stream);
+int vlmclip_gelu_f32_bwd(const float* a, const float* dy, float* da, int64_t n, void* stream);
+/* y = a (* mask) (+ b), mask / b optional: dropout application (mask already scaled by 1/(1-p)) and residual adds */
+int vlmclip_fma_mask_f32(const float* a, const float* mask, const float* b, float* y, int64_t n, void* stream);
+/* Single-query multi-head attention against a table shared by the batch, head_dim 64 (nn.MultiheadAttention's core,
+ * adapter/clip_adapter.py:114): q [B, H*64]; k, v [S, H*64] (row stride ldkv); p_out [B, H, S] = softmax(q k^T scale)
+ * (kept for the backward); pmask (optional) [B, H, S] multiplies p (attention dropout); out [B, H*64] = (p*pmask) v.
+ * Backward: dq [B, H*64], dk / dv [S, H*64] (summed over the batch, WRITTEN); ds_ws: B*H*S floats of workspace. */
+int vlmclip_attn1q_f32_fwd(const float* q, const float* k, const float* v, int64_t ldkv, const float* pmask, float* p_out,
+                           float* out, int B, int S, int H, float scale, void* stream);
+int vlmclip_attn1q_f32_bwd(const float* dout, const float* q, const float* k, const float* v, int64_t ldkv, const float* p,
+                           const float* pmask, float* ds_ws, float* dq, float* dk, float* dv, int B, int S, int H,
+                           float scale, void* stream);
+
 /* bf16 <-> fp32 casts with optional row gather (token-0 slice): y[r, :] = x[r*ldx : r*ldx + D] */
 int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream);
 

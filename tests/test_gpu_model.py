@@ -190,10 +190,10 @@ def test_model_errors_and_api(cuda, clip_b32):
     from vlm_clip_b200 import _native as N
     from vlm_clip_b200.model_m import CLIPWithAdapters
 
-    m = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=True, shared_adapter_layers=1).to(cuda)
     pix, ids, mask = O.synthetic_batch(2)
-    with pytest.raises(N.NativeError):
-        m(input_ids=ids.to(cuda), attention_mask=mask.to(cuda), pixel_values=pix.to(cuda))
+    m_cpu = CLIPWithAdapters(clip=O.build_hf_clip(B32, seed=0, vision_layers=1, text_layers=1), use_shared_adapters=False)
+    with pytest.raises(N.NativeError):  # CPU model / CPU tensors: no fallback
+        m_cpu(input_ids=ids, attention_mask=mask, pixel_values=pix)
     m2 = _make_model(cuda, clip_b32)
     out = m2(input_ids=ids.to(cuda), attention_mask=mask.to(cuda), pixel_values=pix.to(cuda), return_loss=False)
     assert set(out) == {"text_features", "image_features"} and out["image_features"].shape == (2, 512)
@@ -304,7 +304,7 @@ def test_config3_vit_l14_dims_with_peclip_adapters(cuda):
 
 def test_shared_mhs_adapter_inference(cuda, clip_b32):
     """Row 8a-8: the cross-modal adapter's inference path on the GPU against the fp32 oracle, stand-alone and inside
-    CLIPWithAdapters (token-0 evaluation, model_m.py:93-102); training it raises."""
+    CLIPWithAdapters (token-0 evaluation, model_m.py:93-102)."""
     from vlm_clip_b200 import _native as N
     from vlm_clip_b200.adapter.clip_adapter import SharedMHSAttentionAdapter
     from vlm_clip_b200.model_m import CLIPWithAdapters
@@ -319,9 +319,6 @@ def test_shared_mhs_adapter_inference(cuda, clip_b32):
         y = mod(xt, table)
     ref = O.shared_mhs_adapter(xt, table, a)
     assert y.shape == ref.shape and _rel(y, ref) < 1e-2, _rel(y, ref)
-    mod.train()
-    with pytest.raises(N.NativeError):
-        mod(xt, table)
 
     torch.manual_seed(2)
     model = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=True, shared_adapter_layers=2).to(cuda).eval()
@@ -337,6 +334,82 @@ def test_shared_mhs_adapter_inference(cuda, clip_b32):
         hid = O.shared_mhs_adapter(hid, tab, {k: v.detach() for k, v in ad.state_dict().items()})
     ref_t = hid[:, 0] @ sd["text_projection.weight"].t()
     assert _rel(t, ref_t) < FEAT_TOL, _rel(t, ref_t)
+
+
+def test_shared_mhs_adapter_training(cuda, clip_b32):
+    """Row 8a-8, trainable path: output and the gradients of all 18 parameters, of the text rows and of the table against
+    autograd over the fp32 oracle (dropout 0: the reference's dropout is stochastic), then a training-mode run with
+    dropout 0.1, then Track M end to end with two shared adapter layers in the loss."""
+    from vlm_clip_b200.adapter.clip_adapter import SharedMHSAttentionAdapter
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+
+    torch.manual_seed(21)
+    mod = SharedMHSAttentionAdapter(dropout=0.0).to(cuda).train()
+    g = torch.Generator().manual_seed(22)
+    xt = torch.randn(6, 1, 512, generator=g).to(cuda).requires_grad_(True)
+    table = (torch.randn(1, 50, 768, generator=g) * 0.5).to(cuda).requires_grad_(True)
+    w = torch.randn(6, 1, 512, generator=g).to(cuda)
+    y = mod(xt, table)
+    (y * w).sum().backward()
+    a = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    xr, tr_ = xt.detach().clone().requires_grad_(True), table.detach().clone().requires_grad_(True)
+    ref = O.shared_mhs_adapter(xr, tr_, a)
+    (ref * w).sum().backward()
+    assert _rel(y, ref) < 1e-5, _rel(y, ref)          # fp32 path
+    assert _rel(xt.grad, xr.grad) < 1e-4 and _rel(table.grad, tr_.grad) < 1e-4
+    for k, p_ in mod.named_parameters():
+        assert p_.grad is not None and _rel(p_.grad, a[k].grad) < 1e-4, (k, _rel(p_.grad, a[k].grad))
+
+    # dropout 0.1 (adapter/clip_adapter.py:84,96): stochastic in train mode, reproducible under a seed, off in eval mode
+    torch.manual_seed(31)
+    drop = SharedMHSAttentionAdapter().to(cuda).train()
+    torch.manual_seed(5)
+    y1 = drop(xt.detach(), table.detach())
+    torch.manual_seed(5)
+    y2 = drop(xt.detach(), table.detach())
+    y3 = drop(xt.detach(), table.detach())
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    drop.eval()
+    with torch.no_grad():
+        ye = drop(xt.detach(), table.detach())  # bf16 tensor-core inference path
+    ref_e = O.shared_mhs_adapter(xt.detach(), table.detach(), {k: v.detach() for k, v in drop.state_dict().items()})
+    assert _rel(ye, ref_e) < 1e-2
+    assert 1e-3 < _rel(y1, ref_e) < 0.5  # dropped, but the same function in expectation
+
+    # Track M with the reference's default constructor flags (use_shared_adapters=True, two layers), batch > 1
+    torch.manual_seed(2)
+    model = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=True, shared_adapter_layers=2).to(cuda).train()
+    for ad in model.shared_adapters:
+        ad.cross_attn.dropout = 0.0
+        ad.mlp[3].p = 0.0
+    pix, ids, mask = O.synthetic_batch(4, seed=8)
+    ids[:, 0] = torch.arange(4) * 13 + 2
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    out = model(input_ids=ids, attention_mask=mask, pixel_values=pix, return_loss=True)
+    out["loss"].backward()
+    sd = {k: v.detach() for k, v in clip_b32.state_dict().items()}
+    ta = {k: v.detach().clone().requires_grad_(True) for k, v in model.text_adapter.state_dict().items()}
+    va = {k: v.detach().clone().requires_grad_(True) for k, v in model.vision_adapter.state_dict().items()}
+    sa = [{k: v.detach().clone().requires_grad_(True) for k, v in ad.state_dict().items()} for ad in model.shared_adapters]
+    hid = O.seq_adapter(O.text_tower(sd, ids, mask, 8), ta)
+    tab = sd["vision_model.embeddings.position_embedding.weight"].unsqueeze(0)
+    for a_ in sa:
+        hid = O.shared_mhs_adapter(hid, tab, a_)
+    ref_t = hid[:, 0] @ sd["text_projection.weight"].t()
+    ref_i = O.model_m_image_features(sd, 12, pix, va)
+    ref_out = O.contrastive_loss(ref_t, ref_i, sd["logit_scale"])
+    ref_out["loss"].backward()
+    assert abs(out["loss"].item() - ref_out["loss"].item()) < LOSS_TOL
+    assert _rel(out["text_features"], ref_out["text_features"]) < FEAT_TOL
+    for ad, a_ in zip(model.shared_adapters, sa):
+        for k, p_ in ad.named_parameters():
+            gr = a_[k].grad
+            assert p_.grad is not None, k
+            if gr.norm().item() < 1e-12:
+                continue
+            cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), gr.flatten(), dim=0).item()
+            assert cos > 0.97, (k, cos)
+    assert all(p_.grad is None for p_ in model.clip.parameters())
 
 
 def test_full_size_properties_vit_b16_batch256(cuda):

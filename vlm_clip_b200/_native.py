@@ -53,6 +53,13 @@ PROTOTYPES = {
     "vlmclip_l2norm_rows_bwd": (_i, [_p, _p, _p, _i, _i, _p]),
     "vlmclip_adamw_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vlmclip_gather_rows_bf16_to_f32": (_i, [_p, _i64, _p, _i, _i, _p]),
+    "vlmclip_layernorm_f32": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _f, _p]),
+    "vlmclip_layernorm_f32_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
+    "vlmclip_gelu_f32": (_i, [_p, _p, _i64, _p]),
+    "vlmclip_gelu_f32_bwd": (_i, [_p, _p, _p, _i64, _p]),
+    "vlmclip_fma_mask_f32": (_i, [_p, _p, _p, _p, _i64, _p]),
+    "vlmclip_attn1q_f32_fwd": (_i, [_p, _p, _p, _i64, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "vlmclip_attn1q_f32_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "vlmclip_transpose_to_bf16": (_i, [_p, _i, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "vlmclip_cast_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
     "vlmclip_rowsum_bf16": (_i, [_p, _i64, _p, _i, _i, _p]),

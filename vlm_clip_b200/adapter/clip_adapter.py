@@ -66,8 +66,9 @@ class SharedMHSAttentionAdapter(nn.Module):
 
     Parameter layout and state-dict keys match the reference (text_proj, image_proj, cross_attn, norm1..3, mlp).
     The reference can only execute this module at batch size 1 (model_m.py:96-100 passes a batch-1 K/V to
-    nn.MultiheadAttention) and it hard-codes 512/768 widths.  forward() runs the inference path
-    natively; training it raises instead of silently running a non-native path.
+    nn.MultiheadAttention) and it hard-codes 512/768 widths.  forward() runs the bf16 tensor-core
+    inference path under no_grad in eval mode and the fp32 trainable path (fused autograd node, hand-written backward,
+    adapter/shared_train.py) otherwise; both evaluate every text row on its own against the shared table.
     """
 
     def __init__(self, text_input_size=512, image_input_size=768, hidden_size=512, num_heads=8, dropout=0.1):
@@ -102,16 +103,20 @@ class SharedMHSAttentionAdapter(nn.Module):
 
         hidden_states [B, T, text_input_size]; encoder_hidden_states [1, S, image_input_size] (what model_m.py:93-96
         passes: the vision position table, one for the whole batch).  Every text row attends to the table on its own,
-        so the reference's batch-1 limitation does not apply here.  Training this module (dropout, backward through
-        the attention and the table path) has no kernel yet and raises."""
-        if self.training or (torch.is_grad_enabled() and (hidden_states.requires_grad or
-                                                          any(p.requires_grad for p in self.parameters()))):
-            raise N.NativeError(
-                "SharedMHSAttentionAdapter: only the inference path (eval mode under torch.no_grad()) has sm_100a kernels; "
-                "train with CLIPWithAdapters(use_shared_adapters=False) — the configuration the reference itself can train "
-                "(trainer.py:191-195)")
+        so the reference's batch-1 limitation does not apply here.  In training mode, or whenever a gradient is
+        needed, the fp32 trainable path (adapter/shared_train.py) runs instead: same arithmetic, dropout, backward."""
         if encoder_hidden_states.dim() != 3 or encoder_hidden_states.shape[0] != 1:
             raise ValueError("encoder_hidden_states must be [1, S, image_input_size] (one table shared by the batch)")
+        if self.training or (torch.is_grad_enabled() and (hidden_states.requires_grad or encoder_hidden_states.requires_grad
+                                                          or any(p.requires_grad for p in self.parameters()))):
+            # trainable path: fp32, one fused autograd node with a hand-written backward (adapter/shared_train.py);
+            # dropout (adapter/clip_adapter.py:84,96) is active in training mode only
+            from .shared_train import shared_adapter_train
+
+            lead = hidden_states.shape[:-1]
+            rows = hidden_states.reshape(-1, hidden_states.shape[-1]).float().contiguous()
+            out = shared_adapter_train(self, rows, encoder_hidden_states[0].float().contiguous())
+            return out.view(*lead, out.shape[-1])
         D, H = self.text_proj.out_features, self.cross_attn.num_heads
         if D // H != 64:
             raise ValueError("the attention kernel is specialised for head_dim = 64")

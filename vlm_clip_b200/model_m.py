@@ -211,8 +211,8 @@ class CLIPWithAdapters(nn.Module):
             tok0 = self.text_adapter(tok0)
         if self.use_shared_adapters:
             # model_m.py:93-100: every shared adapter attends from the text states to the vision position table; each
-            # text row does so on its own and only token 0 is kept (model_m.py:102), so token 0 alone is evaluated.
-            # Inference only: the adapter raises in training mode (no backward kernels for it).
+            # text row does so on its own and only token 0 is kept (model_m.py:102), so token 0 alone is evaluated
+            # (bf16 tensor-core path under no_grad in eval mode, fp32 trainable path with dropout + backward otherwise).
             table = self.clip.vision_model.embeddings.position_embedding.weight.unsqueeze(0)
             for shared_adapter in self.shared_adapters:
                 tok0 = shared_adapter(tok0.unsqueeze(1), table).squeeze(1)
