@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VLMCLIP_ABI_VERSION 3
+#define VLMCLIP_ABI_VERSION 4
 
 /* activation selector for GEMM epilogues and adapter kernels */
 enum {
@@ -124,6 +124,13 @@ int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const 
  *   A query row whose keys are all masked produces zeros. */
 int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                           float scale, void* stream);
+/* Same operator with a caller-provided scratch buffer of vlmclip_attention_fwd_workspace(B, S, H) floats (0 = none
+ * needed).  With it, unmasked sequences of 225..384 tokens (ViT-L/14: S = 257) run on the tcgen05 kernel as two key
+ * ranges whose partial softmaxes are merged on the device (reference exponent and row sum per row and head live in
+ * the workspace between the two launches); workspace = NULL behaves exactly like vlmclip_attention_fwd. */
+int64_t vlmclip_attention_fwd_workspace(int B, int S, int H);
+int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_t* key_mask, float* workspace, int B, int S,
+                             int H, int causal, float scale, void* stream);
 
 /* Single-query attention, head_dim 64: out[b] = softmax(q[b] K^T * scale) V per head, ONE query row per batch element.
  * Replaces nn.MultiheadAttention's core in SharedMHSAttentionAdapter (adapter/clip_adapter.py:114, as called from

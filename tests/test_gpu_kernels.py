@@ -171,7 +171,10 @@ def test_text_embed(cuda):
 
 
 @pytest.mark.parametrize("B,S,H,causal,masked", [(2, 50, 12, False, False), (3, 197, 12, False, False),
-                                                 (2, 257, 16, False, False), (4, 77, 8, True, False),
+                                                 (2, 257, 16, False, False), (2, 225, 4, False, False),
+                                                 (1, 384, 2, False, False), (3, 300, 16, False, False),
+                                                 (2, 258, 2, False, False),
+                                                 (2, 257, 4, False, True), (4, 77, 8, True, False),
                                                  (4, 77, 8, True, True), (1, 16, 1, True, False),
                                                  (2, 64, 2, False, True)])
 @pytest.mark.parametrize("force_tc", [False, True])
@@ -460,6 +463,83 @@ def test_attention_late_maximum_rescale(cuda, S, late):
     ref = O.attention_core(qf, kf, vf, H, False, None).reshape(B * S, D)
     assert torch.isfinite(out.float()).all()
     assert _rel(out, ref) < 8e-3, f"rel err {_rel(out, ref)}"
+
+
+@pytest.mark.parametrize("S,lo,hi", [(257, 230, 257), (257, 208, 257), (257, 100, 257), (257, 0, 40), (257, 200, 216),
+                                     (257, 256, 257), (384, 300, 384), (225, 224, 225)])
+def test_attention_key_range_split_merge(cuda, S, lo, hi):
+    """224 < S <= 384 runs as two key ranges ([0, 208) and [208, S)) merged in the second launch's epilogue.  Keys
+    [lo, hi) carry logits ~70 nats above the rest, so the two ranges' reference exponents differ by ~100 octaves in
+    either direction (one side's weight underflows to exactly 0) or the dominant keys straddle the boundary."""
+    from vlm_clip_b200 import ops
+
+    B, H = 2, 3
+    D = H * 64
+    g = _gen(S * 7 + lo)
+    q = torch.randn(B, S, H, 64, device=cuda, generator=g) * 0.3
+    k = torch.randn(B, S, H, 64, device=cuda, generator=g) * 0.3
+    v = torch.randn(B, S, H, 64, device=cuda, generator=g)
+    u = torch.randn(H, 64, device=cuda, generator=g)
+    u = u / u.norm(dim=1, keepdim=True) * 8.0
+    q = q + 3.0 * u
+    k[:, lo:hi] = k[:, lo:hi] + 3.0 * u
+    qkv = torch.stack([q, k, v], 2).reshape(B * S, 3 * D).to(bf16)
+    assert ops.N.load().vlmclip_attention_fwd_workspace(B, S, H) == 2 * B * S * H
+    out = ops.attention(qkv, B, S, H)
+    qf, kf, vf = qkv.float().view(B, S, 3, D).unbind(2)
+    ref = O.attention_core(qf, kf, vf, H, False, None).reshape(B * S, D)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 8e-3, f"rel err {_rel(out, ref)}"
+    # the workspace-free entry point keeps these shapes on the mma.sync kernel: same oracle, independent kernel
+    out2 = torch.empty_like(out)
+    rc = ops.N.load().vlmclip_attention_fwd(ops.N.ptr(qkv), ops.N.ptr(out2), None, B, S, H, 0, 0.125, ops.N.stream())
+    assert rc == 0
+    assert _rel(out2, ref) < 8e-3
+    assert _rel(out, out2.float()) < 8e-3
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+def test_attention_key_range_split_variants_subprocess(variant):
+    """VLMCLIP_ATTN_SPLIT selects the variant of the split (1: every row on the tcgen05 kernel, per-thread merge loads;
+    2: tail rows on the single-query kernel, staged merge; 3: every row on the tcgen05 kernel, staged merge).  The
+    switch is read once per process, so each variant is held to the oracle in a fresh one."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import torch, sys
+sys.path.insert(0, '.')
+from oracle import clip_oracle as O
+from vlm_clip_b200 import ops
+dev = torch.device('cuda:0')
+worst = 0.0
+for (B, S, H, lo, hi) in [(2, 257, 16, 0, 0), (2, 225, 4, 0, 0), (1, 384, 2, 0, 0), (3, 300, 16, 0, 0), (2, 258, 2, 0, 0),
+                          (40, 257, 16, 0, 0), (2, 257, 3, 230, 257), (2, 257, 3, 0, 40), (2, 257, 3, 200, 216)]:
+    g = torch.Generator(device='cuda').manual_seed(B * 1000 + S)
+    D = H * 64
+    qkv = torch.randn(B * S, 3, H, 64, device=dev, generator=g)
+    if hi > lo:  # dominant keys on one side of / across the range boundary (see test_attention_key_range_split_merge)
+        u = torch.randn(H, 64, device=dev, generator=g)
+        u = u / u.norm(dim=1, keepdim=True) * 8.0
+        qkv = qkv.view(B, S, 3, H, 64) * 0.3
+        qkv[:, :, 2] /= 0.3
+        qkv[:, :, 0] += 3.0 * u
+        qkv[:, lo:hi, 1] += 3.0 * u
+    qkv = qkv.reshape(B * S, 3 * D).to(torch.bfloat16)
+    out = ops.attention(qkv, B, S, H)
+    q, k, v = qkv.float().view(B, S, 3, D).unbind(2)
+    ref = O.attention_core(q, k, v, H, False, None).reshape(B * S, D)
+    assert torch.isfinite(out.float()).all()
+    worst = max(worst, ((out.float() - ref).norm() / ref.norm()).item())
+assert worst < 8e-3, worst
+print('ok', worst)
+"""
+    env = dict(os.environ, VLMCLIP_ATTN_SPLIT=variant)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
 
 
 @pytest.mark.parametrize("hs,ws,h,patch,bgr", [(60, 80, 32, 16, False), (32, 32, 32, 16, True), (45, 61, 28, 14, False)])

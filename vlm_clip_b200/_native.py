@@ -37,6 +37,8 @@ PROTOTYPES = {
     "vlmclip_vision_embed_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "vlmclip_text_embed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "vlmclip_attention_fwd_workspace": (_i64, [_i, _i, _i]),
+    "vlmclip_attention_fwd_ws": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "vlmclip_attention_1q": (_i, [_p, _i64, _p, _p, _i64, _i64, _p, _i, _i, _i, _f, _p]),
     "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "vlmclip_adapter_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),

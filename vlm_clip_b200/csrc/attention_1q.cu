@@ -20,7 +20,7 @@ constexpr int Q1_MAX_KEYS_PER_LANE = 16;  // S <= 512
 __global__ void __launch_bounds__(Q1_WARPS * 32)
 attention_1q_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_stride, const __nv_bfloat16* __restrict__ k,
                     const __nv_bfloat16* __restrict__ v, int64_t kv_row_stride, int64_t kv_batch_stride,
-                    __nv_bfloat16* __restrict__ out, int B, int S, int H, float scale_log2e) {
+                    __nv_bfloat16* __restrict__ out, int64_t out_stride, int B, int S, int H, float scale_log2e) {
   pdl_wait();
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,34 +76,56 @@ attention_1q_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_stride, const
   for (int i = 0; i < Q1_MAX_KEYS_PER_LANE; ++i) {
     if (i * 32 < S) {  // warp-uniform
       const int nj = min(32, S - i * 32);
-      for (int jj = 0; jj < nj; ++jj) {
+      const __nv_bfloat16* vrow = vp + (int64_t)(i * 32) * kv_row_stride + lane * 2;
+      int jj = 0;
+      for (; jj + 8 <= nj; jj += 8) {  // eight independent 128-byte row loads in flight per warp
+        uint32_t raw[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) raw[e] = *reinterpret_cast<const uint32_t*>(vrow + (int64_t)(jj + e) * kv_row_stride);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pj = __shfl_sync(0xffffffffu, sc[i], jj + e);
+          o0 = fmaf(pj, bf16_lo(raw[e]), o0);
+          o1 = fmaf(pj, bf16_hi(raw[e]), o1);
+        }
+      }
+      for (; jj < nj; ++jj) {
         const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
-        const uint32_t raw = *reinterpret_cast<const uint32_t*>(vp + (int64_t)(i * 32 + jj) * kv_row_stride + lane * 2);
+        const uint32_t raw = *reinterpret_cast<const uint32_t*>(vrow + (int64_t)jj * kv_row_stride);
         o0 = fmaf(pj, bf16_lo(raw), o0);
         o1 = fmaf(pj, bf16_hi(raw), o1);
       }
     }
   }
   const float inv = l > 0.f ? 1.f / l : 0.f;
-  *reinterpret_cast<uint32_t*>(out + (int64_t)b * H * 64 + h * 64 + lane * 2) = pack_bf16x2(o0 * inv, o1 * inv);
+  *reinterpret_cast<uint32_t*>(out + (int64_t)b * out_stride + h * 64 + lane * 2) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
 }  // namespace
-}  // namespace vlmclip
 
-using namespace vlmclip;
-
-extern "C" int vlmclip_attention_1q(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
-                                    int64_t kv_batch_stride, void* out, int B, int S, int H, float scale, void* stream) {
+// Output row b at out + b * out_stride elements (the C entry point below: out_stride = H * 64; the key-range split of
+// attention_pp.cu: the tail rows of every sequence inside the [B*S, D] attention output).
+int attention_1q_strided(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
+                         int64_t kv_batch_stride, void* out, int64_t out_stride, int B, int S, int H, float scale,
+                         cudaStream_t stream) {
   VLMCLIP_CHECK_ARG(q && k && v && out, "attention_1q: null pointer");
   VLMCLIP_CHECK_ARG(B > 0 && H > 0 && S > 0 && S <= 32 * Q1_MAX_KEYS_PER_LANE, "attention_1q: bad dims B=%d S=%d H=%d", B, S, H);
-  VLMCLIP_CHECK_ARG(q_stride % 8 == 0 && kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && (uintptr_t)q % 16 == 0 &&
-                        (uintptr_t)k % 16 == 0 && (uintptr_t)v % 4 == 0 && (uintptr_t)out % 4 == 0,
+  VLMCLIP_CHECK_ARG(q_stride % 8 == 0 && kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && out_stride % 2 == 0 &&
+                        (uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)v % 4 == 0 && (uintptr_t)out % 4 == 0,
                     "attention_1q: strides must be multiples of 8 elements and pointers 16-byte aligned");
   count_launch(1);
   const int grid = (B * H + Q1_WARPS - 1) / Q1_WARPS;
-  return report_cuda(launch_pdl(attention_1q_kernel, dim3(grid), dim3(Q1_WARPS * 32), 0, (cudaStream_t)stream, 1,
+  return report_cuda(launch_pdl(attention_1q_kernel, dim3(grid), dim3(Q1_WARPS * 32), 0, stream, 1,
                                 (const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                kv_row_stride, kv_batch_stride, (__nv_bfloat16*)out, B, S, H, scale * 1.4426950408889634f),
+                                kv_row_stride, kv_batch_stride, (__nv_bfloat16*)out, out_stride, B, S, H,
+                                scale * 1.4426950408889634f),
                      "attention_1q_kernel launch");
+}
+
+}  // namespace vlmclip
+
+extern "C" int vlmclip_attention_1q(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
+                                    int64_t kv_batch_stride, void* out, int B, int S, int H, float scale, void* stream) {
+  return vlmclip::attention_1q_strided(q, q_stride, k, v, kv_row_stride, kv_batch_stride, out, (int64_t)H * 64, B, S, H,
+                                       scale, (cudaStream_t)stream);
 }

@@ -25,6 +25,10 @@
 
 namespace vlmclip {
 void count_launch(int n);
+// attention_1q.cu: one query row per batch element, output row b at out + b * out_stride
+int attention_1q_strided(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
+                         int64_t kv_batch_stride, void* out, int64_t out_stride, int B, int S, int H, float scale,
+                         cudaStream_t stream);
 
 namespace {
 
@@ -35,7 +39,6 @@ constexpr uint32_t PP_Q_TILE_BYTES = PP_M * PP_HD * 2;  // 16 KB
 constexpr int PP_TMEM_COLS = 512;
 constexpr int PP_O_COL = 448;
 constexpr int PP_MAX_STAGES = 4;
-constexpr int PP_MAX_NPAD = 224;
 
 struct PPParams {
   const uint8_t* key_mask;
@@ -54,6 +57,16 @@ struct PPParams {
   int nstage;
   uint32_t out_stage_off;  // 16 KB output staging tile
   int debug;
+  // key-range split for 224 < S <= 432 (ViT-L/14, S = 257): a launch covers keys [key0, key0 + Sk) of every sequence.
+  // The first launch (key0 = 0) also writes each row's softmax reference exponent and row sum to `stats`
+  // ([B*S][H] float2), the second one (merge = 1) combines its own un-normalised O with the first launch's
+  // normalised output in its epilogue: out = (O1 a1 + O2 2^(off2-m)) / (a1 + l2 2^(off2-m)), a1 = l1 2^(off1-m).
+  // merge = 1: each thread loads its own row after O has arrived; merge = 2: the tile is staged through shared memory
+  // with row-contiguous loads issued before the wait for O (the epilogue warpgroup is serial over tiles).
+  // Sq: query rows [0, Sq) of every sequence are computed (Sq = S except when a caller handles tail rows elsewhere).
+  int Sk, key0, merge, Sq;
+  int q_loads;  // TMA loads per unit for Q (box = 128 * mtiles / q_loads rows; the box dimension limit is 256)
+  float2* stats;
 };
 
 // visibility bits of keys [k0, k0+32) for query row qrow
@@ -63,7 +76,7 @@ __device__ __forceinline__ uint32_t key_bits32(const PPParams& p, const uint8_t*
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int key = k0 + j;
-    bool ok = key < p.S;
+    bool ok = key < p.Sk;
     if (GENERAL_MASK) {
       if (p.causal) ok = ok && key <= qrow;
       if (km != nullptr && ok) ok = __ldg(km + key) != 0;
@@ -80,7 +93,7 @@ template <bool GENERAL_MASK>
 __device__ __forceinline__ void max_chunk(const PPParams& p, const uint32_t (&cur)[32], int k0, int kmax_warp,
                                           const uint8_t* km, int qrow, float (&m4)[4]) {
   if (k0 >= kmax_warp) return;
-  if (!GENERAL_MASK && k0 + 32 <= p.S) {
+  if (!GENERAL_MASK && k0 + 32 <= p.Sk) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(cur[j]));
   } else {
@@ -100,7 +113,7 @@ __device__ __forceinline__ void exp_chunk(const PPParams& p, const uint32_t (&cu
   if (k0 >= kmax_warp) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = 0u;
-  } else if (!GENERAL_MASK && k0 + 32 <= p.S) {
+  } else if (!GENERAL_MASK && k0 + 32 <= p.Sk) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const uint32_t e0 = __float_as_uint(fast_exp2(fmaf(__uint_as_float(cur[2 * j]), c, -off))) & 0xffff0000u;
@@ -170,7 +183,10 @@ __device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t 
   exp_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, c, off, l4, tb + ch * 16);
 }
 
-template <bool GENERAL_MASK>
+// SPLIT: role of the launch in a two-launch key-range split (PPParams::stats / merge), compiled per role so that the
+// plain kernel carries none of it: 0 = not split, 1 = first range (publishes the row statistics), 2 = second range
+// with merge = 1, 3 = second range with merge = 2
+template <bool GENERAL_MASK, int SPLIT>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const PPParams p) {
@@ -186,6 +202,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_free = s_full + 7;                // [1] O drained to registers (128 arrivals), in tile order
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
   float* s_l = reinterpret_cast<float*>(s_full + 10);  // [2][128] row sums, softmax -> epilogue
+  float* s_off = s_l + 256;                            // [2][128] reference exponents (key-range split only)
   uint8_t* s_out = smem + p.out_stage_off;             // [128 rows][128 B] bf16 O tile, 16-B chunks XOR-swizzled by row
 
   const int warp = threadIdx.x >> 5;
@@ -237,9 +254,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint8_t* st = stage0 + sg * p.stage_bytes;
         mbar_wait(&kv_empty[sg], ((u / p.nstage) & 1) ^ 1u);
         mbar_arrive_expect_tx(&kv_full[sg], p.q_bytes + 2 * p.kv_bytes);
-        tma_load_2d(st, &tmQ, &kv_full[sg], h * PP_HD, bb * p.S);
-        tma_load_2d(st + p.q_bytes, &tmKV, &kv_full[sg], p.D + h * PP_HD, bb * p.S);
-        tma_load_2d(st + p.q_bytes + p.kv_stride, &tmKV, &kv_full[sg], 2 * p.D + h * PP_HD, bb * p.S);
+        const uint32_t q_part = p.q_bytes / (uint32_t)p.q_loads;
+        for (int ql = 0; ql < p.q_loads; ++ql)
+          tma_load_2d(st + ql * q_part, &tmQ, &kv_full[sg], h * PP_HD, bb * p.S + ql * (int)(q_part >> 7));
+        tma_load_2d(st + p.q_bytes, &tmKV, &kv_full[sg], p.D + h * PP_HD, bb * p.S + p.key0);
+        tma_load_2d(st + p.q_bytes + p.kv_stride, &tmKV, &kv_full[sg], 2 * p.D + h * PP_HD, bb * p.S + p.key0);
       }
     }
   } else if (warp == 1) {
@@ -288,12 +307,102 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     long long tk[3] = {0, 0, 0};
     const bool dbg = p.debug == 1 && blockIdx.x == 0 && wq == 0 && lane == 0;
+    // Second key range: the rows and statistics the merge folds in were written by the previous launch and stream from
+    // DRAM (the attention output of a ViT-L/14 batch is larger than L2; measured ~3000 clk per tile when loaded on
+    // demand by this serial warpgroup).  Each thread requests its row of a later tile into L2 ahead of time.
+    constexpr int PF_TILES = 2;
+    auto prefetch_merge_rows = [&](int tt) {
+      if (tt >= n_tiles) return;
+      const int pu = tt / p.mtiles, pmt = tt - pu * p.mtiles;
+      const int pbh = blockIdx.x + pu * gridDim.x;
+      const int pb = pbh / p.H, ph = pbh - pb * p.H;
+      const int pr = pmt * PP_M + r_local;
+      if (pr < p.Sq) {
+        prefetch_l2(p.out + ((int64_t)pb * p.S + pr) * p.D + ph * PP_HD);
+        prefetch_l2(p.stats + ((int64_t)pb * p.S + pr) * p.H + ph);
+      }
+    };
+    if (SPLIT >= 2) {
+      for (int tt = 0; tt < PF_TILES; ++tt) prefetch_merge_rows(tt);
+    }
     for (int t = 0; t < n_tiles; ++t) {
       long long t0 = dbg ? clock64() : 0;
+      if (SPLIT >= 2) prefetch_merge_rows(t + PF_TILES);
       const int u = t / p.mtiles, mt = t - u * p.mtiles;
       const int bh = blockIdx.x + u * gridDim.x;
       const int bb = bh / p.H, h = bh - bb * p.H;
-      const bool warp_valid = (mt * PP_M + wq * 32) < p.S;  // warp-uniform
+      const bool warp_valid = (mt * PP_M + wq * 32) < p.Sq;  // warp-uniform
+      if (SPLIT == 3) {
+        // ---- second key range, staged variant: the first launch's tile is copied into the staging tile with the
+        // row-contiguous access pattern of the stores below (4 rows x 128 B per warp instruction instead of 32 lines of
+        // 16 B), requested before the wait for O; each thread then folds its own row in place, O in two 32-column halves
+        const int qr = mt * PP_M + r_local;
+        const int chunk = lane & 7;
+        float2 st1 = make_float2(0.f, 0.f);
+        if (warp_valid && qr < p.Sq) st1 = p.stats[((int64_t)bb * p.S + qr) * p.H + h];  // (off1, l1)
+        uint4 pv[8];
+        {
+          const __nv_bfloat16* pbase = p.out + ((int64_t)bb * p.S) * p.D + h * PP_HD + chunk * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pr = mt * PP_M + wq * 32 + k * 4 + (lane >> 3);
+            pv[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (pr < p.Sq) pv[k] = *reinterpret_cast<const uint4*>(pbase + (int64_t)pr * p.D);
+          }
+        }
+        epi_bar_sync();  // the previous tile's stores have read the staging tile
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = wq * 32 + k * 4 + (lane >> 3);
+          *reinterpret_cast<uint4*>(s_out + r * 128 + ((chunk ^ (r & 7)) << 4)) = pv[k];
+        }
+        mbar_wait(o_full, t & 1);
+        tcgen05_fence_after();
+        if (dbg) { long long x = clock64(); tk[0] += x - t0; t0 = x; }
+        mbar_wait(&p_full[t & 1], (t >> 1) & 1);  // already complete (it precedes O); orders the read of the row sums
+        const float l = s_l[(t & 1) * 128 + r_local];
+        const float off2 = s_off[(t & 1) * 128 + r_local];
+        mbar_arrive(&e_done[t & 1]);
+        const bool h1 = st1.y > 0.f, h2 = l > 0.f;
+        const float m = fmaxf(h1 ? st1.x : -INFINITY, h2 ? off2 : -INFINITY);
+        const float a1 = h1 ? st1.y * exp2f(st1.x - m) : 0.f;
+        const float s2 = h2 ? exp2f(off2 - m) : 0.f;
+        const float den = a1 + l * s2;
+        const float inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
+        const float w1 = a1 * inv, w2 = s2 * inv;
+        epi_bar_sync();  // the first launch's tile is staged
+        uint8_t* srow = s_out + r_local * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t oh[32];
+          if (warp_valid) {
+            __syncwarp();
+            tmem_ld_32x32b_x32(tmem_base + lane_off + PP_O_COL + half * 32, oh);
+            tmem_wait_ld();
+          }
+          if (half == 1) {
+            tcgen05_fence_before();
+            mbar_arrive(o_free);  // O is in registers: the next P.V may start
+          }
+          if (warp_valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4* slot = reinterpret_cast<uint4*>(srow + (((half * 4 + q) ^ (r_local & 7)) << 4));
+              const uint4 pq = *slot;
+              const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+              uint32_t ow[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = fmaf(bf16_lo(pw[e]), w1, __uint_as_float(oh[q * 8 + 2 * e]) * w2);
+                const float hi = fmaf(bf16_hi(pw[e]), w1, __uint_as_float(oh[q * 8 + 2 * e + 1]) * w2);
+                ow[e] = pack_bf16x2(lo, hi);
+              }
+              *slot = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+          }
+        }
+        if (dbg) { long long x = clock64(); tk[1] += x - t0; t0 = x; }
+      } else {
       mbar_wait(o_full, t & 1);
       tcgen05_fence_after();
       if (dbg) { long long x = clock64(); tk[0] += x - t0; t0 = x; }
@@ -308,10 +417,44 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_arrive(o_free);  // O is in registers: the next P.V may start
       mbar_wait(&p_full[t & 1], (t >> 1) & 1);  // already complete (it precedes O); orders the read of the row sums
       const float l = s_l[(t & 1) * 128 + r_local];
+      const float off2 = SPLIT != 0 ? s_off[(t & 1) * 128 + r_local] : 0.f;
       mbar_arrive(&e_done[t & 1]);
       epi_bar_sync();  // the previous tile's stores have read the staging tile
       if (dbg) { long long x = clock64(); tk[1] += x - t0; t0 = x; }
-      if (warp_valid) {
+      if (SPLIT == 2 && warp_valid) {
+        // second key range: fold the first launch's normalised rows (already in `out`) into this tile
+        const int qr = mt * PP_M + r_local;
+        uint8_t* srow = s_out + r_local * 128;
+        float a1 = 0.f, s2 = 0.f, inv = 0.f;
+        const __nv_bfloat16* prev = p.out + ((int64_t)bb * p.S + (qr < p.Sq ? qr : 0)) * p.D + h * PP_HD;
+        if (qr < p.Sq) {
+          const float2 st1 = p.stats[((int64_t)bb * p.S + qr) * p.H + h];  // (off1, l1)
+          const bool h1 = st1.y > 0.f, h2 = l > 0.f;
+          const float m = fmaxf(h1 ? st1.x : -INFINITY, h2 ? off2 : -INFINITY);
+          a1 = h1 ? st1.y * exp2f(st1.x - m) : 0.f;
+          s2 = h2 ? exp2f(off2 - m) : 0.f;
+          const float den = a1 + l * s2;
+          inv = den > 0.f ? __fdividef(1.f, den) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint4 pv = make_uint4(0u, 0u, 0u, 0u);
+          if (qr < p.Sq) pv = *reinterpret_cast<const uint4*>(prev + q * 8);
+          const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = fmaf(bf16_lo(pw[e]), a1, __uint_as_float(o[q * 8 + 2 * e]) * s2) * inv;
+            const float hi = fmaf(bf16_hi(pw[e]), a1, __uint_as_float(o[q * 8 + 2 * e + 1]) * s2) * inv;
+            ow[e] = pack_bf16x2(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(srow + ((q ^ (r_local & 7)) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+      } else if (warp_valid) {
+        if (SPLIT == 1) {
+          const int qr = mt * PP_M + r_local;
+          if (qr < p.Sq) p.stats[((int64_t)bb * p.S + qr) * p.H + h] = make_float2(off2, l);
+        }
         const float inv = l > 0.f ? __fdividef(1.f, l) : 0.f;
         uint8_t* srow = s_out + r_local * 128;
 #pragma unroll
@@ -324,6 +467,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           *reinterpret_cast<uint4*>(srow + ((q ^ (r_local & 7)) << 4)) = v;
         }
       }
+      }
       epi_bar_sync();  // the whole O tile is in smem
       {
         // 4 warps x 32 rows; one store instruction = 4 rows x 128 contiguous bytes (8 lanes per row)
@@ -333,7 +477,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < 8; ++k) {
           const int r = wq * 32 + k * 4 + (lane >> 3);
           const int qr = mt * PP_M + r;
-          if (qr < p.S) {
+          if (qr < p.Sq) {
             const uint4 v = *reinterpret_cast<const uint4*>(s_out + r * 128 + ((chunk ^ (r & 7)) << 4));
             st_v4(obase + (int64_t)qr * p.D, v);
           }
@@ -366,15 +510,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int bh = blockIdx.x + u * gridDim.x;
       const int bb = bh / p.H;
       const int qrow = mt * PP_M + r_local;
-      const bool warp_valid = (mt * PP_M + wq * 32) < p.S;  // warp-uniform
+      const bool warp_valid = (mt * PP_M + wq * 32) < p.Sq;  // warp-uniform
       const uint8_t* km = p.key_mask != nullptr ? p.key_mask + (int64_t)bb * p.S : nullptr;
-      const int kmax_warp = p.causal ? min(p.S, mt * PP_M + wq * 32 + 32) : p.S;  // keys any row of this warp sees
+      const int kmax_warp = p.causal ? min(p.Sk, mt * PP_M + wq * 32 + 32) : p.Sk;  // keys any row of this warp sees
       const uint32_t par = (t >> 1) & 1;
 
       mbar_wait(&s_full[wg], par);
       tcgen05_fence_after();
       if (dbg) { long long x = clock64(); tk[0] += x - t0; t0 = x; }
       float l = 0.f;
+      float off_pub = 0.f;
       if (warp_valid) {
         __syncwarp();
         // ---- single pass over S (TMEM reads are the scarce resource: ~64 B/clk/SM): softmax is shift invariant, so the
@@ -406,10 +551,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        off_pub = off;
       }
       if (dbg) { long long x = clock64(); tk[3] += x - t0; t0 = x; }
       mbar_wait(&e_done[wg], par ^ 1u);  // the epilogue has read the row sums of tile t-2
       s_l[wg * 128 + r_local] = l;
+      if (SPLIT != 0) s_off[wg * 128 + r_local] = off_pub;
       if (warp_valid) tmem_wait_st();
       tcgen05_fence_before();
       mbar_arrive(&p_full[wg]);
@@ -429,17 +576,17 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <bool GENERAL_MASK>
+template <bool GENERAL_MASK, int SPLIT>
 int launch_pp(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const PPParams& p, size_t smem, int grid, cudaStream_t s) {
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(attention_pp_kernel<GENERAL_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLMCLIP_CUDA(cudaFuncSetAttribute(attention_pp_kernel<GENERAL_MASK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  cudaError_t e = launch_pdl(attention_pp_kernel<GENERAL_MASK>, dim3(grid), dim3(PP_THREADS), smem, s, 1, tmQ, tmKV, p);
+  cudaError_t e = launch_pdl(attention_pp_kernel<GENERAL_MASK, SPLIT>, dim3(grid), dim3(PP_THREADS), smem, s, 1, tmQ, tmKV, p);
   if (e != cudaSuccess) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, attention_pp_kernel<GENERAL_MASK>);
+    cudaFuncGetAttributes(&fa, attention_pp_kernel<GENERAL_MASK, SPLIT>);
     set_last_error("attention_pp_kernel launch: %s (regs=%d maxThreads=%d static_smem=%zu requested_dyn=%zu grid=%d)",
                    cudaGetErrorString(e), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, smem, grid);
     return (int)e;
@@ -447,11 +594,9 @@ int launch_pp(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const PPParams& p
   return 0;
 }
 
-}  // namespace
-
-// S <= 224; called by vlmclip_attention_fwd (attention_tc.cu), arguments already validated there
-int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal, float scale,
-                           cudaStream_t s) {
+// One launch over keys [key0, key0 + Sk) of every sequence (Sk <= 224).  stats / merge: see PPParams.
+int launch_range(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int Sq, int H, int causal,
+                 float scale, int key0, int Sk, float2* stats, int merge, cudaStream_t s) {
   PPParams p;
   p.key_mask = key_mask;
   p.out = (__nv_bfloat16*)out;
@@ -461,9 +606,15 @@ int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, 
   p.D = H * PP_HD;
   p.causal = causal;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.Npad = (S + 15) / 16 * 16;
+  p.Sk = Sk;
+  p.Sq = Sq;
+  p.key0 = key0;
+  p.merge = merge;
+  p.stats = stats;
+  p.Npad = (Sk + 15) / 16 * 16;
   p.nb = (p.Npad + 31) / 32 * 32;
-  p.mtiles = (S + PP_M - 1) / PP_M;
+  p.mtiles = (Sq + PP_M - 1) / PP_M;
+  p.q_loads = p.mtiles <= 2 ? 1 : p.mtiles;
   p.num_units = B * H;
   p.q_bytes = (uint32_t)p.mtiles * PP_Q_TILE_BYTES;
   p.kv_bytes = (uint32_t)p.Npad * 128u;
@@ -473,25 +624,72 @@ int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, 
     const char* e = getenv("VLMCLIP_ATTN_DEBUG");
     p.debug = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  int nstage = (int)((208u * 1024u) / p.stage_bytes);  // 227 KB - 16 KB output tile - barriers / row sums
+  int nstage = (int)((206u * 1024u) / p.stage_bytes);  // 227 KB - 16 KB output tile - barriers / row sums / exponents
   p.nstage = nstage < 2 ? 2 : (nstage > PP_MAX_STAGES ? PP_MAX_STAGES : nstage);
-  const size_t ctrl = (2 * PP_MAX_STAGES + 10) * 8 + 256 * sizeof(float) + 16;
+  const size_t ctrl = (2 * PP_MAX_STAGES + 10) * 8 + 512 * sizeof(float) + 16;
   p.out_stage_off = (uint32_t)(((size_t)p.nstage * p.stage_bytes + ctrl + 1023) & ~(size_t)1023);
   const size_t smem = (size_t)p.out_stage_off + PP_M * 128;
   if (smem > 232448) {
-    set_last_error("attention: S=%d needs %zu bytes of shared memory", S, smem);
+    set_last_error("attention: S=%d (keys %d..%d) needs %zu bytes of shared memory", S, key0, key0 + Sk, smem);
     return -1;
   }
   CUtensorMap tmQ, tmKV;
   const int64_t rows = (int64_t)B * S;
-  int rc = make_tmap_bf16(&tmQ, qkv, rows, 3 * (int64_t)p.D, 3 * (int64_t)p.D, PP_M * p.mtiles);
+  int rc = make_tmap_bf16(&tmQ, qkv, rows, 3 * (int64_t)p.D, 3 * (int64_t)p.D, PP_M * p.mtiles / p.q_loads);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmKV, qkv, rows, 3 * (int64_t)p.D, 3 * (int64_t)p.D, p.Npad);
   if (rc) return rc;
   const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
   count_launch(1);
   const bool general = causal != 0 || key_mask != nullptr;
-  return general ? launch_pp<true>(tmQ, tmKV, p, smem, grid, s) : launch_pp<false>(tmQ, tmKV, p, smem, grid, s);
+  if (stats != nullptr) {
+    if (general) {
+      set_last_error("attention: the key-range split does not take a mask");
+      return -1;
+    }
+    return merge == 0   ? launch_pp<false, 1>(tmQ, tmKV, p, smem, grid, s)
+           : merge == 1 ? launch_pp<false, 2>(tmQ, tmKV, p, smem, grid, s)
+                        : launch_pp<false, 3>(tmQ, tmKV, p, smem, grid, s);
+  }
+  return general ? launch_pp<true, 0>(tmQ, tmKV, p, smem, grid, s) : launch_pp<false, 0>(tmQ, tmKV, p, smem, grid, s);
+}
+
+}  // namespace
+
+// S <= 224; called by vlmclip_attention_fwd (attention_tc.cu), arguments already validated there
+int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal, float scale,
+                           cudaStream_t s) {
+  return launch_range(qkv, out, key_mask, B, S, S, H, causal, scale, 0, S, nullptr, 0, s);
+}
+
+// 224 < S <= 384, no mask (ViT-L/14: S = 257): two launches over the key ranges [0, 208) and [208, S); the second one
+// merges in its epilogue (see PPParams).  workspace: 2 * B * S * H floats (reference exponent and row sum per row and
+// head).  208 keys, not 224: with three 128-query tiles per unit two pipeline stages of Q + K + V must fit 227 KB.
+// A sequence that is a few rows longer than a multiple of 128 (257 = 2 * 128 + 1) would spend a whole 128-row tile
+// slot per unit on those rows: they go to the one-warp-per-row kernel of attention_1q.cu instead (variant 2).
+//   variant 1: every row on the tcgen05 kernel, merge = 1
+//   variant 2: tail rows on the single-query kernel, merge = 2
+//   variant 3: every row on the tcgen05 kernel, merge = 2
+constexpr int PP_SPLIT_KEYS = 208;
+constexpr int PP_MAX_TAIL_ROWS = 2;
+int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, int B, int S, int H, float scale,
+                                 int variant, cudaStream_t s) {
+  const int tail = S % PP_M;
+  const int Sq = (variant == 2 && tail >= 1 && tail <= PP_MAX_TAIL_ROWS) ? S - tail : S;
+  float2* stats = reinterpret_cast<float2*>(workspace);
+  int rc = launch_range(qkv, out, nullptr, B, S, Sq, H, 0, scale, 0, PP_SPLIT_KEYS, stats, 0, s);
+  if (rc) return rc;
+  rc = launch_range(qkv, out, nullptr, B, S, Sq, H, 0, scale, PP_SPLIT_KEYS, S - PP_SPLIT_KEYS, stats,
+                    variant == 1 ? 1 : 2, s);
+  if (rc) return rc;
+  const int64_t D = (int64_t)H * PP_HD;
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+  for (int r = Sq; r < S; ++r) {
+    rc = attention_1q_strided(base + r * 3 * D, S * 3 * D, base + D, base + 2 * D, 3 * D, S * 3 * D,
+                              static_cast<__nv_bfloat16*>(out) + r * D, S * D, B, S, H, scale, s);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 }  // namespace vlmclip

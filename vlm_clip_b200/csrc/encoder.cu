@@ -25,7 +25,9 @@ extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, 
     rc = vlmclip_gemm_bf16(x, D, L.qkv_w, D, qkv, 3 * (int64_t)D, L.qkv_b, nullptr, 0, stats, L.qkv_c, nullptr, 0, eps,
                            nullptr, M, 3 * D, D, VLMCLIP_ACT_NONE, 0, stream);
     if (rc) return rc;
-    rc = vlmclip_attention_fwd(qkv, att, key_mask, B, S, H, causal, scale, stream);
+    // `part` is dead between the LN1 combine above and the out-proj epilogue below and holds M * D / 16 >= 2 * M * H
+    // floats: it doubles as the scratch of the key-range split (S = 257)
+    rc = vlmclip_attention_fwd_ws(qkv, att, key_mask, part, B, S, H, causal, scale, stream);
     if (rc) return rc;
     // x += out_proj(att), in place; the epilogue leaves the LN2 partials
     rc = vlmclip_gemm_bf16(att, D, L.out_w, D, x, D, L.out_b, x, D, nullptr, nullptr, nullptr, 0, eps, part, M, D, D,

@@ -260,10 +260,13 @@ def attention(qkv, B: int, S: int, H: int, causal=False, key_mask=None, scale=No
              "attention: key_mask must be uint8 [B,S]")
     if out is None:
         out = torch.empty((B * S, H * 64), device=qkv.device, dtype=bf16)
+    lib = N.load()
+    n_ws = 0 if (causal or key_mask is not None) else lib.vlmclip_attention_fwd_workspace(B, S, H)
+    ws = torch.empty(n_ws, device=qkv.device, dtype=f32) if n_ws > 0 else None
     N.check(
-        N.load().vlmclip_attention_fwd(N.ptr(qkv), N.ptr(out), N.ptr(key_mask), B, S, H, 1 if causal else 0,
-                                       float(scale if scale is not None else 64 ** -0.5), N.stream()),
-        "vlmclip_attention_fwd")
+        lib.vlmclip_attention_fwd_ws(N.ptr(qkv), N.ptr(out), N.ptr(key_mask), N.ptr(ws), B, S, H, 1 if causal else 0,
+                                     float(scale if scale is not None else 64 ** -0.5), N.stream()),
+        "vlmclip_attention_fwd_ws")
     return out
 
 
