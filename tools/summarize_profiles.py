@@ -66,15 +66,18 @@ def report(rep, name, title, labels):
     (OUT / name).write_text("\n".join(out) + "\n")
     return hdr, units, data
 
-launch_summary()
-hdr, units, data = report("prof_gemm.ncu-rep", f"{tag}_gemm_layer.txt",
-                          "tcgen05 GEMM, the four launches of vision layer 5 (ViT-B/16, B=256, M=50432)",
-                          ["qkv(fold)", "out(+res)", "fc1(fold+gelu)", "fc2(+res)"])
-r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 def mb(v, u): return float(v.replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[u]
-per = [mb(d[r], units[r]) + mb(d[w], units[w]) for d in data]
-json.dump({"kernel": "gemm_bf16_tn_kernel", "source": f"profiles/{tag}_gemm_layer.txt (ncu --set full, vision layer 5)",
-           "launches": ["qkv", "out_proj", "fc1", "fc2"], "dram_bytes": per,
-           "dram_bytes_per_launch": sum(per) / len(per)}, open(OUT / "gemm_traffic.json", "w"), indent=1)
-report("prof_attn.ncu-rep", f"{tag}_attention_pp.txt", "tcgen05 ping-pong attention, vision (B=256, S=197, H=12)", ["vision"])
-print("ok")
+
+
+if __name__ == "__main__":
+    launch_summary()
+    hdr, units, data = report("prof_gemm.ncu-rep", f"{tag}_gemm_layer.txt",
+                              "tcgen05 GEMM, the four launches of vision layer 5 (ViT-B/16, B=256, M=50432)",
+                              ["qkv(fold)", "out(+res)", "fc1(fold+gelu)", "fc2(+res)"])
+    r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    per = [mb(d[r], units[r]) + mb(d[w], units[w]) for d in data]
+    json.dump({"kernel": "gemm_bf16_tn_kernel", "source": f"profiles/{tag}_gemm_layer.txt (ncu --set full, vision layer 5)",
+               "launches": ["qkv", "out_proj", "fc1", "fc2"], "dram_bytes": per,
+               "dram_bytes_per_launch": sum(per) / len(per)}, open(OUT / "gemm_traffic.json", "w"), indent=1)
+    report("prof_attn.ncu-rep", f"{tag}_attention_pp.txt", "tcgen05 ping-pong attention, vision (B=256, S=197, H=12)", ["vision"])
+    print("ok")
