@@ -1,5 +1,6 @@
-// tcgen05 attention for 224 < S <= 384 without a mask (ViT-L/14: S = 257) in ONE launch: out = softmax(q k^T * scale) v,
-// head_dim 64.  HF modeling_clip.py:261-279 (eager_attention_forward), :318-331 (dispatch).
+// tcgen05 attention for 225 <= S <= 258 without a mask (ViT-L/14: S = 257) in ONE launch: out = softmax(q k^T * scale) v,
+// head_dim 64 (longer sequences need a third query tile per unit and no longer fit two pipeline stages: they stay on
+// the two-launch split).  HF modeling_clip.py:261-279 (eager_attention_forward), :318-331 (dispatch).
 //
 // STATUS: EXPERIMENTAL.  Compiles for sm_100a, has NOT run on a GPU yet (the round's GPU budget ended first).  It is
 // reachable only with VLMCLIP_ATTN_SPLIT=4; the default for these shapes is the verified two-launch split of
@@ -464,12 +465,11 @@ attention_kr_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-}  // namespace
-
-// 224 < S <= 384, no mask.  Returns -1 with the error string set when the shape does not fit.
-int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, float scale, cudaStream_t s) {
-  KRParams p;
-  p.out = (__nv_bfloat16*)out;
+// Shapes and shared-memory plan; false when S is outside 225..384 or two pipeline stages do not fit.  Two stages are a
+// protocol requirement, not a tuning choice: S of the NEXT unit is issued before the current unit's last P.V, so with
+// one stage the issuer would wait for operands that can only be loaded after that P.V released the stage
+// (tools/kr_protocol_sim.py reproduces the deadlock).
+static bool kr_plan(int B, int S, int H, float scale, KRParams& p, size_t& smem) {
   p.B = B;
   p.S = S;
   p.H = H;
@@ -489,10 +489,7 @@ int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, flo
     nb = max(nb, (p.Npad[r] + 31) / 32 * 32);
   }
   p.nb = nb;
-  if (S <= 224 || S > 32 * KR_MAX_KEYS_PER_LANE || 2 * nb + 2 * KR_HD > KR_TMEM_COLS) {
-    set_last_error("attention (key ranges): S=%d is outside 225..384", S);
-    return -1;
-  }
+  if (S <= 224 || S > 32 * KR_MAX_KEYS_PER_LANE || 2 * nb + 2 * KR_HD > KR_TMEM_COLS) return false;
   p.kv_rows = (S + 15) / 16 * 16;
   p.kv_loads = p.kv_rows > 256 ? 2 : 1;
   p.num_units = B * H;
@@ -502,14 +499,32 @@ int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, flo
   p.stage_bytes = p.q_bytes + p.qt_bytes + 2 * p.kv_bytes;
   const size_t ctrl = KR_NBAR * 8 + 16 + 512 * sizeof(float);
   const size_t budget = 232448 - KR_M * 128 - ctrl - 1024;
-  int nstage = (int)(budget / p.stage_bytes);
+  const int nstage = (int)(budget / p.stage_bytes);
   p.nstage = nstage > KR_MAX_STAGES ? KR_MAX_STAGES : nstage;
-  if (p.nstage < 1) {
-    set_last_error("attention (key ranges): S=%d needs %u bytes of shared memory per stage", S, p.stage_bytes);
+  if (p.nstage < 2) return false;
+  p.out_stage_off = (uint32_t)(((size_t)p.nstage * p.stage_bytes + ctrl + 1023) & ~(size_t)1023);
+  smem = (size_t)p.out_stage_off + KR_M * 128;
+  return true;
+}
+
+}  // namespace
+
+// whether attention_fwd_keyranges takes sequences of S tokens (S = 257: yes; S >= 289: K + V + three query tiles no
+// longer fit twice)
+bool attention_keyranges_supported(int S) {
+  KRParams p;
+  size_t smem = 0;
+  return kr_plan(1, S, 1, 1.f, p, smem);
+}
+
+int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, float scale, cudaStream_t s) {
+  KRParams p;
+  size_t smem = 0;
+  if (!kr_plan(B, S, H, scale, p, smem)) {
+    set_last_error("attention (key ranges): S=%d is not supported by the single-launch kernel", S);
     return -1;
   }
-  p.out_stage_off = (uint32_t)(((size_t)p.nstage * p.stage_bytes + ctrl + 1023) & ~(size_t)1023);
-  const size_t smem = (size_t)p.out_stage_off + KR_M * 128;
+  p.out = (__nv_bfloat16*)out;
   CUtensorMap tmQ, tmQt, tmKV;
   const int64_t rows = (int64_t)B * S;
   int rc = make_tmap_bf16(&tmQ, qkv, rows, 3 * (int64_t)p.D, 3 * (int64_t)p.D, KR_M);

@@ -18,6 +18,7 @@ int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, 
 int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, int B, int S, int H, float scale,
                                  int variant, cudaStream_t stream);
 int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, float scale, cudaStream_t stream);
+bool attention_keyranges_supported(int S);
 
 }  // namespace vlmclip
 
@@ -59,7 +60,8 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
     const char* e = getenv("VLMCLIP_ATTN_FORCE_TC");
     return e != nullptr && e[0] == '1';
   }();
-  if (workspace != nullptr && split_eligible(S, causal, key_mask) && split_variant() == 4)
+  if (workspace != nullptr && split_eligible(S, causal, key_mask) && split_variant() == 4 &&
+      attention_keyranges_supported(S))
     return attention_fwd_keyranges(qkv, out, B, S, H, scale, s);
   if (workspace != nullptr && split_eligible(S, causal, key_mask))
     return attention_fwd_pingpong_split(qkv, out, workspace, B, S, H, scale, split_variant(), s);
