@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VLMCLIP_ABI_VERSION 4
+#define VLMCLIP_ABI_VERSION 5
 
 /* activation selector for GEMM epilogues and adapter kernels */
 enum {
@@ -71,6 +71,16 @@ int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
                       const float* bias, const void* residual, int64_t ldr, const float* row_stats,
                       const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
                       float* stats_part_out, int M, int N, int K, int act, int out_fp32, void* stream);
+/* Two-term residual update of an encoder layer (HF modeling_clip.py:372-373, 382-383 `hidden_states = residual +
+ * hidden_states`), in place:  x += A[M,K] * W[N,K]^T + bias, where the residual stream x is stored as TWO bf16 planes,
+ * hi = bf16(x) at X and lo = bf16(x - hi) at X + plane_stride elements (both [M, N], leading dimension ldx).  hi is
+ * what the next dense layer reads as its bf16 A operand; lo restores 16 mantissa bits on the one tensor that is
+ * accumulated over all layers, which takes the towers' end-to-end error from 9e-3 (bf16 stream) to 3.5e-3 (the floor
+ * set by the bf16 operand roundings any bf16 execution has).  stats_part_out as in vlmclip_gemm_bf16, computed from
+ * the fp32 values before they are split. */
+int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
+                           int64_t plane_stride, const float* bias, float* stats_part_out, int M, int N, int K,
+                           void* stream);
 
 /* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */
@@ -108,13 +118,14 @@ int vlmclip_mean_pool_bwd(const float* dy, float* dx, int B, int T, int P, void*
  *   x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p]; y = LN(x).
  *   patch: [B*(S-1), D], fp32 (patch_bf16 = 0: the patch GEMM ran with out_fp32 = 1) or bf16 (patch_bf16 = 1: the
  *   patch GEMM's bf16 output, half the traffic; what an autocast reference run produces); the position add and the
- *   LayerNorm are fp32 either way.  cls fp32[D]; pos fp32[S,D]; y bf16 [B*S, D]. */
+ *   LayerNorm are fp32 either way.  cls fp32[D]; pos fp32[S,D]; y bf16 [B*S, D]; y_lo (optional) bf16 [B*S, D]
+ *   receives bf16(value - y), the second term of the two-term residual stream (vlmclip_gemm_bf16_res2). */
 int vlmclip_vision_embed_ln(const void* patch, int patch_bf16, const float* cls, const float* pos, const float* gamma,
-                            const float* beta, void* y, int B, int S, int D, float eps, void* stream);
+                            const float* beta, void* y, void* y_lo, int B, int S, int D, float eps, void* stream);
 /* Text embeddings (HF:234-258): y[b,s] = tok[ids[b,s]] + pos[s].  ids int64 [B,S]; tok fp32[V,D]
- * or bf16 (tok_bf16=1); pos fp32 [>=S, D]; y bf16 [B*S, D].  Out-of-range ids -> return -1 is NOT possible
+ * or bf16 (tok_bf16=1); pos fp32 [>=S, D]; y bf16 [B*S, D]; y_lo optional (see vlmclip_vision_embed_ln).  Out-of-range ids -> return -1 is NOT possible
  * without a sync, so ids are clamped to [0,V) on device (the reference would raise IndexError). */
-int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y, int B,
+int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y, void* y_lo, int B,
                        int S, int D, int V, void* stream);
 
 /* Multi-head self-attention core (HF:261-279,318-331): softmax(q k^T * scale + mask) v, fp32 softmax.
@@ -160,7 +171,9 @@ typedef struct {
   const void* fc2_w; /* bf16 [D, F] */
   const float* fc2_b;
 } vlmclip_layer_t;
-int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* qkv, void* att, void* hid,
+/* x_lo (optional): second plane of the two-term residual stream, bf16 [B*S, D] (see vlmclip_gemm_bf16_res2); NULL keeps
+ * the stream in one bf16 plane (half the residual traffic, 2.5x the end-to-end rounding error). */
+int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* x_lo, void* qkv, void* att, void* hid,
                         float* stats, float* part, const uint8_t* key_mask, int B, int S, int H, int D, int F, float eps,
                         int causal, int act, void* stream);
 
@@ -316,6 +329,8 @@ int vlmclip_attn1q_f32_bwd(const float* dout, const float* q, const float* k, co
 
 /* bf16 <-> fp32 casts with optional row gather (token-0 slice): y[r, :] = x[r*ldx : r*ldx + D] */
 int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream);
+/* same from a two-term stream: y[r, :] = float(x[r*ldx ...]) + float(x_lo[r*ldx ...]) (x_lo may be NULL) */
+int vlmclip_gather_rows2_bf16_to_f32(const void* x, const void* x_lo, int64_t ldx, float* y, int R, int D, void* stream);
 
 #ifdef __cplusplus
 }

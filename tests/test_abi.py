@@ -51,7 +51,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.vlmclip_abi_version() == 4
+    assert lib.vlmclip_abi_version() == 5
     assert isinstance(lib.vlmclip_last_error(), bytes)
     assert lib.vlmclip_launch_count() >= 0
     # argument validation happens before any CUDA call, so it can be exercised without a GPU

@@ -100,6 +100,74 @@ def test_gemm_emits_and_consumes_ln_partials(cuda):
     assert _rel(y, ref) < 6e-3, _rel(y, ref)
 
 
+RES2_CASES = [
+    # M, N, K   (pair kernel: M > 128 and N > 128; single-CTA wide / narrow variants below that)
+    (1000, 768, 768),     # out-proj, M tail
+    (50432 // 8, 768, 3072),  # fc2 shape (an eighth of the ViT-B/16 batch), many tiles per CTA pair
+    (2048, 512, 2048),    # text fc2 (narrow-tile decision for N = 512)
+    (771, 1024, 1024),    # L/14 out-proj, odd M
+    (100, 768, 768),      # M < 128: single-CTA wide tile
+    (96, 128, 512),       # narrow tile
+]
+
+
+@pytest.mark.parametrize("M,N,K", RES2_CASES)
+@pytest.mark.parametrize("cfg", [None, "43", "61"])
+def test_gemm_res2_two_term_residual(cuda, M, N, K, cfg, monkeypatch):
+    """vlmclip_gemm_bf16_res2: x (hi + lo planes) += a w^T + bias in place, plus LN partials of the fp32 result.
+    hi must be the bf16 rounding of the fp32 result and hi + lo must carry it to ~2^-16."""
+    import subprocess, sys, os
+
+    from vlm_clip_b200 import ops
+
+    if cfg is not None:
+        # the stage / panel configuration is read once per process: exercise the alternatives in a child process
+        if (M, N, K) != RES2_CASES[0]:
+            pytest.skip("alternative pipeline configurations are checked on one shape")
+        env = dict(os.environ, VLMCLIP_GEMM_RES2_CFG=cfg)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k",
+                            "test_gemm_res2_two_term_residual and None and 1000"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    g = _gen(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, device=cuda, generator=g).to(bf16)
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(bf16)
+    bias = torch.randn(N, device=cuda, generator=g)
+    x = torch.randn(M, N, device=cuda, generator=g) * 3 + 1.5
+    x2 = torch.empty(2, M, N, device=cuda, dtype=bf16)
+    x2[0] = x.to(bf16)
+    x2[1] = (x - x2[0].float()).to(bf16)
+    x_in = x2[0].float() + x2[1].float()
+    part = torch.zeros(M, N // 32, 2, device=cuda)
+    ref = a.float() @ w.float().t() + bias + x_in
+    ops.gemm_res2(a, w, bias, x2, stats_part_out=part)
+    torch.cuda.synchronize()
+    hi, lo = x2[0].float(), x2[1].float()
+    assert torch.isfinite(hi).all() and torch.isfinite(lo).all()
+    # fp32 accumulation order differs from torch's: a few fp32 ulps of |ref| ~ 10
+    assert _rel(hi + lo, ref) < 3e-5, _rel(hi + lo, ref)
+    assert _rel(hi, ref) < 4e-3
+    # hi is the nearest bf16 of the value that was split (lo is at most half a bf16 ulp of hi)
+    assert ((hi + lo).to(bf16).float() - hi).abs().max().item() <= 2.0 ** -7 * hi.abs().max().item()
+    assert (lo.abs() <= hi.abs() * 2.0 ** -8 + 1e-30).float().mean().item() > 0.999
+    blocks = ref.view(M, N // 32, 32)
+    ref_mean = blocks.mean(-1)
+    ref_m2 = (blocks - ref_mean[..., None]).pow(2).sum(-1)
+    assert torch.allclose(part[..., 0], ref_mean, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(part[..., 1], ref_m2, rtol=1e-3, atol=1e-3)
+
+
+def test_gemm_res2_rejects_overlapping_planes(cuda):
+    from vlm_clip_b200 import _native as N
+
+    a = torch.zeros(256, 64, device=cuda, dtype=bf16)
+    w = torch.zeros(256, 64, device=cuda, dtype=bf16)
+    x = torch.zeros(2 * 256 * 256, device=cuda, dtype=bf16)
+    b = torch.zeros(256, device=cuda)
+    rc = N.load().vlmclip_gemm_bf16_res2(N.ptr(a), 64, N.ptr(w), 64, N.ptr(x), 256, 128, N.ptr(b), None, 256, 256, 64, N.stream())
+    assert rc < 0 and b"overlap" in N.load().vlmclip_last_error()
+
+
 def test_gemm_rejects_bad_args(cuda):
     from vlm_clip_b200 import ops
 
@@ -155,6 +223,11 @@ def test_im2col_and_embed(cuda, patch, dt):
     y16 = ops.vision_embed_ln(p16, cls, pos, gamma, beta, B, S)
     x16 = torch.cat([cls.expand(B, 1, D), p16.float().view(B, S - 1, D)], 1) + pos[None]
     assert _rel(y16.view(B, S, D), O.layer_norm(x16, gamma, beta)) < 4e-3
+    # two-term output: hi is the same tensor, hi + lo restores the fp32 value to ~2^-16
+    lo = torch.empty_like(y16)
+    hi = ops.vision_embed_ln(p16, cls, pos, gamma, beta, B, S, out_lo=lo)
+    assert torch.equal(hi, y16)
+    assert _rel((hi.float() + lo.float()).view(B, S, D), O.layer_norm(x16, gamma, beta)) < 2e-5
 
 
 def test_text_embed(cuda):
@@ -168,6 +241,12 @@ def test_text_embed(cuda):
     y = ops.text_embed(ids, tok, pos)
     ref = (tok[ids] + pos[None]).to(bf16).view(B * S, D)
     assert torch.equal(y, ref)
+    lo = torch.empty_like(y)
+    hi = ops.text_embed(ids, tok, pos, out_lo=lo)
+    assert torch.equal(hi, ref)
+    assert _rel(hi.float() + lo.float(), (tok[ids] + pos[None]).view(B * S, D)) < 2e-5
+    rows = ops.gather_rows_f32(hi, B, S * D, D, lo=lo)  # token 0 of every sequence, both terms
+    assert torch.equal(rows, (hi.float() + lo.float()).view(B, S, D)[:, 0])
 
 
 @pytest.mark.parametrize("B,S,H,causal,masked", [(2, 50, 12, False, False), (3, 197, 12, False, False),

@@ -26,6 +26,7 @@ PROTOTYPES = {
     "vlmclip_last_error": (C.c_char_p, []),
     "vlmclip_launch_count": (_i64, []),
     "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _i, _f, _p, _i, _i, _i, _i, _i, _p]),
+    "vlmclip_gemm_bf16_res2": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _i, _i, _i, _p]),
     "vlmclip_layernorm_bf16": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_layernorm_bf16_f32out": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _f, _p]),
     "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),
@@ -34,13 +35,13 @@ PROTOTYPES = {
     "vlmclip_preprocess_patches": (_i, [_p, _i64, _i, _i, _i, _p, _p, _f, _f, _f, _f, _f, _f, _p, _i, _i, _i, _i, _p]),
     "vlmclip_mean_pool": (_i, [_p, _p, _i, _i, _i, _p]),
     "vlmclip_mean_pool_bwd": (_i, [_p, _p, _i, _i, _i, _p]),
-    "vlmclip_vision_embed_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
-    "vlmclip_text_embed": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "vlmclip_vision_embed_ln": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
+    "vlmclip_text_embed": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_attention_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "vlmclip_attention_fwd_workspace": (_i64, [_i, _i, _i]),
     "vlmclip_attention_fwd_ws": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "vlmclip_attention_1q": (_i, [_p, _i64, _p, _p, _i64, _i64, _p, _i, _i, _i, _f, _p]),
-    "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
+    "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "vlmclip_adapter_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "vlmclip_adapter_bwd_workspace": (_i64, [_i, _i, _i]),
     "vlmclip_adapter_bwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
@@ -55,6 +56,7 @@ PROTOTYPES = {
     "vlmclip_l2norm_rows_bwd": (_i, [_p, _p, _p, _i, _i, _p]),
     "vlmclip_adamw_clip_step": (_i, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p, _p, _p, _p]),
     "vlmclip_gather_rows_bf16_to_f32": (_i, [_p, _i64, _p, _i, _i, _p]),
+    "vlmclip_gather_rows2_bf16_to_f32": (_i, [_p, _p, _i64, _p, _i, _i, _p]),
     "vlmclip_layernorm_f32": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_layernorm_f32_bwd": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "vlmclip_gelu_f32": (_i, [_p, _p, _i64, _p]),

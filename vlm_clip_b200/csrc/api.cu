@@ -97,6 +97,31 @@ int make_tmap_bf16_box(CUtensorMap* map, const void* base, int64_t rows, int64_t
   return 0;
 }
 
+int make_tmap_bf16_planes(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane_stride,
+                          int planes, int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
+    return -2;
+  }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(plane_stride) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(planes)};
+  const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (base=%p rows=%lld cols=%lld ld=%lld plane=%lld)",
+                   (int)r, base, (long long)rows, (long long)cols, (long long)ld, (long long)plane_stride);
+    return -3;
+  }
+  return 0;
+}
+
 }  // namespace vlmclip
 
 extern "C" int vlmclip_abi_version(void) { return VLMCLIP_ABI_VERSION; }

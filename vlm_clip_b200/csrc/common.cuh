@@ -34,6 +34,10 @@ int sm_count();
 int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int make_tmap_bf16_box(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                        int box_cols);
+// `planes` bf16 matrices [rows, cols] (ld elements) `plane_stride` elements apart -> 3-D map, box
+// [planes x box_rows x box_cols] (one TMA instruction moves the same panel of every plane)
+int make_tmap_bf16_planes(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t plane_stride,
+                          int planes, int box_rows, int box_cols);
 
 // ------------------------------------------------------------------------------------------
 // generic helpers
@@ -172,6 +176,19 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 3-D variants (c0 = innermost coordinate): used for the two-plane (hi, lo) residual panels of the GEMM epilogue
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

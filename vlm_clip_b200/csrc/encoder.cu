@@ -5,7 +5,7 @@
 #include "../../include/vlmclip.h"
 #include "common.cuh"
 
-extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* qkv, void* att, void* hid,
+extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* x_lo, void* qkv, void* att, void* hid,
                                    float* stats, float* part, const uint8_t* key_mask, int B, int S, int H, int D, int F,
                                    float eps, int causal, int act, void* stream) {
   using namespace vlmclip;
@@ -13,6 +13,10 @@ extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, 
   VLMCLIP_CHECK_ARG(B > 0 && S > 0 && H > 0 && D == H * 64 && F > 0 && D % 32 == 0, "encoder_fwd: bad dims");
   const int M = B * S;
   const int npart = D / 32;
+  // two-term residual stream: x = hi plane, x_lo = lo plane (any distance apart, as long as it is a multiple of 8 elements)
+  const int64_t plane = x_lo != nullptr ? (static_cast<const __nv_bfloat16*>(x_lo) - static_cast<const __nv_bfloat16*>(x)) : 0;
+  VLMCLIP_CHECK_ARG(x_lo == nullptr || (plane >= (int64_t)M * D && plane % 8 == 0),
+                    "encoder_fwd: x_lo must follow x by at least B*S*D elements (multiple of 8)");
   const float scale = 0.125f;  // head_dim 64
   int rc = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -30,16 +34,18 @@ extern "C" int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, 
     rc = vlmclip_attention_fwd_ws(qkv, att, key_mask, part, B, S, H, causal, scale, stream);
     if (rc) return rc;
     // x += out_proj(att), in place; the epilogue leaves the LN2 partials
-    rc = vlmclip_gemm_bf16(att, D, L.out_w, D, x, D, L.out_b, x, D, nullptr, nullptr, nullptr, 0, eps, part, M, D, D,
-                           VLMCLIP_ACT_NONE, 0, stream);
+    rc = x_lo != nullptr ? vlmclip_gemm_bf16_res2(att, D, L.out_w, D, x, D, plane, L.out_b, part, M, D, D, stream)
+                         : vlmclip_gemm_bf16(att, D, L.out_w, D, x, D, L.out_b, x, D, nullptr, nullptr, nullptr, 0, eps, part,
+                                             M, D, D, VLMCLIP_ACT_NONE, 0, stream);
     if (rc) return rc;
     rc = vlmclip_ln_partials_to_stats(part, stats, M, npart, eps, stream);
     if (rc) return rc;
     rc = vlmclip_gemm_bf16(x, D, L.fc1_w, D, hid, F, L.fc1_b, nullptr, 0, stats, L.fc1_c, nullptr, 0, eps, nullptr, M, F,
                            D, act, 0, stream);
     if (rc) return rc;
-    rc = vlmclip_gemm_bf16(hid, F, L.fc2_w, F, x, D, L.fc2_b, x, D, nullptr, nullptr, nullptr, 0, eps, part, M, D, F,
-                           VLMCLIP_ACT_NONE, 0, stream);
+    rc = x_lo != nullptr ? vlmclip_gemm_bf16_res2(hid, F, L.fc2_w, F, x, D, plane, L.fc2_b, part, M, D, F, stream)
+                         : vlmclip_gemm_bf16(hid, F, L.fc2_w, F, x, D, L.fc2_b, x, D, nullptr, nullptr, nullptr, 0, eps, part,
+                                             M, D, F, VLMCLIP_ACT_NONE, 0, stream);
     if (rc) return rc;
   }
   return 0;

@@ -67,13 +67,15 @@ struct GemmParams {
 // EB = panel buffers per epilogue group.  EB = 1: one 16 KB panel per group (residual in / result out chained through
 // it).  EB = 2: two panels per group, so the residual panel of the next quarter is prefetched while the current one is
 // processed (used for the residual layers, traded against one pipeline stage of the main loop).
-template <int BLOCK_N, int STAGES, int EB, bool PAIR = false>
+// RP = planes per panel: 1 (bf16 residual / result) or 2 (two-term hi + lo residual stream, EPI_RES2).
+template <int BLOCK_N, int STAGES, int EB, bool PAIR = false, int RP = 1>
 struct SmemLayout {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // a CTA pair splits W along N
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;               // 2 * EB x 16 KB, 1024-aligned
-  static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EB * EBUF_BYTES;   // bias[BLOCK_N], col_c[BLOCK_N] fp32
+  static constexpr uint32_t PANEL_BYTES = RP * EBUF_BYTES;                    // 8 KB per plane
+  static constexpr uint32_t EBUF_OFFSET = STAGES * STAGE_BYTES;               // 2 * EB panels, 1024-aligned
+  static constexpr uint32_t VEC_OFFSET = EBUF_OFFSET + 2 * EB * PANEL_BYTES;  // bias[BLOCK_N], col_c[BLOCK_N] fp32
   static constexpr uint32_t BAR_OFFSET = VEC_OFFSET + 2 * BLOCK_N * 4;
   static constexpr uint32_t NUM_BARS = 2 * STAGES + 4 + 4 * EB;
   static constexpr uint32_t DYN_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16;
@@ -141,14 +143,22 @@ __device__ __forceinline__ void epi_math8(float* v, const float* sBias, const fl
 //   EPI_FOLD_ACT  LN fold + bias + quick_gelu        (fc1)
 //   EPI_RES       bias + residual + LN partials out  (out-proj, fc2)
 //   EPI_PLAIN     bf16 store only                    (patch embedding)
-enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3, EPI_PLAIN = 4 };
+//   EPI_RES2      bias + TWO-TERM residual + LN partials out (out-proj, fc2 of the towers): the residual stream is
+//                 kept as x = hi + lo, two bf16 planes [2][M][N]; hi (= bf16(x)) is what the next GEMM reads as its A
+//                 operand, lo (= bf16(x - hi)) is touched by these epilogues only.  16 mantissa bits instead of 8 on the
+//                 quantity that is accumulated over 2 x L layers: the end-to-end error drops from 9e-3 to the 3.5e-3 of
+//                 the bf16 operand roundings (oracle/emulate_bf16.py).  A panel is then [2 planes][128 rows][32 columns],
+//                 moved by ONE 3-D TMA box per direction.
+enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3, EPI_PLAIN = 4, EPI_RES2 = 5 };
 
 template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                     const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR>;
+  constexpr int RP = EPI == EPI_RES2 ? 2 : 1;
+  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR, RP>;
+  constexpr uint32_t PANEL_BYTES = L::PANEL_BYTES;
   constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 or 512)
   constexpr int QUARTERS = BLOCK_N / QUARTER_N;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -172,11 +182,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader
   // epilogue switches: compile-time constants for the specialised instantiations
   const bool k_staged = EPI == EPI_GENERIC ? p.staged != 0 : true;
-  const bool k_has_res = EPI == EPI_GENERIC ? p.residual != nullptr : EPI == EPI_RES;
+  const bool k_has_res = EPI == EPI_GENERIC ? p.residual != nullptr : (EPI == EPI_RES || EPI == EPI_RES2);
   const bool k_has_bias = EPI == EPI_GENERIC ? p.bias != nullptr : EPI != EPI_PLAIN;
   const bool k_has_stats = EPI == EPI_GENERIC ? (p.row_stats != nullptr || p.part_in != nullptr)
                                               : (EPI == EPI_FOLD || EPI == EPI_FOLD_ACT);
-  const bool k_part_out = EPI == EPI_GENERIC ? p.part_out != nullptr : (EPI == EPI_RES && p.part_out != nullptr);
+  const bool k_part_out =
+      EPI == EPI_GENERIC ? p.part_out != nullptr : ((EPI == EPI_RES || EPI == EPI_RES2) && p.part_out != nullptr);
   const int k_act = EPI == EPI_GENERIC ? p.act : (EPI == EPI_FOLD_ACT ? 1 : 0);
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker index (CTA or CTA pair)
   const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -328,12 +339,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         r0 = (PAIR ? 2 * m_t + (int)cta_rank : m_t) * BLOCK_M;
       };
       auto hand_over = [&](const QIter& it, int j) {  // make panel j ready for unit `it`
-        uint8_t* ebuf = sE + (g * EB + j) * EBUF_BYTES;
+        uint8_t* ebuf = sE + (g * EB + j) * PANEL_BYTES;
         if (k_has_res) {
           int c0, r0;
           coords(it, c0, r0);
-          mbar_arrive_expect_tx(&res_full_bar[g * EB + j], EBUF_BYTES);
-          tma_load_2d(ebuf, &tmR, &res_full_bar[g * EB + j], c0, r0);
+          mbar_arrive_expect_tx(&res_full_bar[g * EB + j], PANEL_BYTES);
+          if (RP == 2)
+            tma_load_3d(ebuf, &tmR, &res_full_bar[g * EB + j], c0, r0, 0);  // both planes of the stream in one box
+          else
+            tma_load_2d(ebuf, &tmR, &res_full_bar[g * EB + j], c0, r0);
         } else {
           mbar_arrive(&res_full_bar[g * EB + j]);
         }
@@ -347,11 +361,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (uint32_t n = 0; st.tile < num_tiles; ++n) {
         const int j = n % EB;
-        uint8_t* ebuf = sE + (g * EB + j) * EBUF_BYTES;
+        uint8_t* ebuf = sE + (g * EB + j) * PANEL_BYTES;
         int c0, r0;
         coords(st, c0, r0);
         mbar_wait(&e_written_bar[g * EB + j], (n / EB) & 1u);  // the group has written quarter n into panel j
-        tma_store_2d(&tmC, ebuf, c0, r0);
+        if (RP == 2)
+          tma_store_3d(&tmC, ebuf, c0, r0, 0);
+        else
+          tma_store_2d(&tmC, ebuf, c0, r0);
         tma_store_commit();
         advance(st);
         if (ld.tile < num_tiles) {
@@ -457,19 +474,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int pj = qseq % EB;
             mbar_wait(&res_full_bar[g * EB + pj], (qseq / EB) & 1u);  // panel is ours (and holds the residual, if any)
             if (dbg) { long long t = clock64(); tk[3] += t - t0; t0 = t; }
-            uint8_t* erow = sE + (g * EB + pj) * EBUF_BYTES + row_in_tile * 64;
+            uint8_t* erow = sE + (g * EB + pj) * PANEL_BYTES + row_in_tile * 64;
             float sh = 0.f, s1 = 0.f, s2 = 0.f;  // shifted one-pass statistics of this row's 32 outputs
             // All shared-memory READS of the panel (residual) and of the staged vectors come first, the four 16-byte
             // result stores last: generic smem pointers may alias as far as the compiler knows, so a store between two
             // chunks would serialise their loads and math (measured: 1.8 k cycles per panel instead of ~0.6 k).
-            uint4 rr[4];
+            uint4 rr[4], rl[4];
             uint4* slot[4];
+            constexpr int LO = EBUF_BYTES / 16;  // uint4 stride from a hi slot to its lo slot (second plane of the panel)
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
               slot[pc] = reinterpret_cast<uint4*>(erow + ((pc ^ ((row_in_tile >> 1) & 3)) << 4));  // 64-B swizzle
               if (k_has_res) rr[pc] = *slot[pc];
+              if (RP == 2) rl[pc] = *(slot[pc] + LO);
             }
-            uint4 o[4];
+            uint4 o[4], ol[4];
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
               float v[8];
@@ -486,6 +505,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[6] += bf16_lo(rr[pc].w);
                 v[7] += bf16_hi(rr[pc].w);
               }
+              if (RP == 2) {
+                v[0] += bf16_lo(rl[pc].x);
+                v[1] += bf16_hi(rl[pc].x);
+                v[2] += bf16_lo(rl[pc].y);
+                v[3] += bf16_hi(rl[pc].y);
+                v[4] += bf16_lo(rl[pc].z);
+                v[5] += bf16_hi(rl[pc].z);
+                v[6] += bf16_lo(rl[pc].w);
+                v[7] += bf16_hi(rl[pc].w);
+              }
               if (k_part_out) {
                 if (pc == 0) sh = v[0];  // shift by the first value: keeps sum((v - sh)^2) - s1^2/n well conditioned
 #pragma unroll
@@ -499,10 +528,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o[pc].y = pack_bf16x2(v[2], v[3]);
               o[pc].z = pack_bf16x2(v[4], v[5]);
               o[pc].w = pack_bf16x2(v[6], v[7]);
+              if (RP == 2) {  // lo = bf16(v - hi): the part of the fp32 value the hi plane cannot hold
+                ol[pc].x = pack_bf16x2(v[0] - bf16_lo(o[pc].x), v[1] - bf16_hi(o[pc].x));
+                ol[pc].y = pack_bf16x2(v[2] - bf16_lo(o[pc].y), v[3] - bf16_hi(o[pc].y));
+                ol[pc].z = pack_bf16x2(v[4] - bf16_lo(o[pc].z), v[5] - bf16_hi(o[pc].z));
+                ol[pc].w = pack_bf16x2(v[6] - bf16_lo(o[pc].w), v[7] - bf16_hi(o[pc].w));
+              }
             }
             if (dbg) { long long t = clock64(); tk[5] += t - t0; t0 = t; }
 #pragma unroll
-            for (int pc = 0; pc < 4; ++pc) *slot[pc] = o[pc];
+            for (int pc = 0; pc < 4; ++pc) {
+              *slot[pc] = o[pc];
+              if (RP == 2) *(slot[pc] + LO) = ol[pc];
+            }
             if (k_part_out && row_ok) {
               const float mq = s1 * (1.f / 32.f);
               reinterpret_cast<float2*>(p.part_out)[(int64_t)row * (p.N >> 5) + (c0 >> 5)] =
@@ -596,7 +634,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                 GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR>;
+  using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR, EPI == EPI_RES2 ? 2 : 1>;
   static bool attr_set = false;  // benign race: setting the attribute twice is harmless
   if (!attr_set) {
     VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>,
@@ -758,4 +796,72 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   }
   VLMCLIP_GEMM_LAUNCH(128, 6, 2, false)
 #undef VLMCLIP_GEMM_LAUNCH
+}
+
+// x (two planes: hi at X, lo at X + plane_stride) += A W^T + bias, in place; optional LayerNorm partials of the updated
+// rows.  The out-proj / fc2 step of an encoder layer (HF modeling_clip.py:372-383) on the two-term residual stream.
+extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
+                                      int64_t plane_stride, const float* bias, float* stats_part_out, int M, int N, int K,
+                                      void* stream) {
+  VLMCLIP_CHECK_ARG(A && W && X && bias, "gemm_res2: null A/W/X/bias pointer");
+  VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_res2: non-positive dims M=%d N=%d K=%d", M, N, K);
+  VLMCLIP_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm_res2: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  VLMCLIP_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldx % 8 == 0 && plane_stride % 8 == 0,
+                    "gemm_res2: lda/ldw/ldx/plane_stride must be multiples of 8");
+  VLMCLIP_CHECK_ARG(lda >= K && ldw >= K && ldx >= N, "gemm_res2: leading dimension smaller than row length");
+  VLMCLIP_CHECK_ARG(plane_stride >= (int64_t)(M - 1) * ldx + N, "gemm_res2: the two planes overlap");
+  VLMCLIP_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0) && ((uintptr_t)X % 16 == 0) &&
+                        ((uintptr_t)bias % 16 == 0),
+                    "gemm_res2: A/W/X/bias must be 16-byte aligned");
+  VLMCLIP_CHECK_ARG(stats_part_out == nullptr || N % 32 == 0, "gemm_res2: stats_part_out needs N %% 32 == 0");
+
+  GemmParams p{};
+  p.C = X;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(X);
+  p.part_out = stats_part_out;
+  p.ln_eps = 0.f;
+  p.ldc = ldx;
+  p.ldr = ldx;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.staged = 1;
+  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  static const int dbg_flag = []() {
+    const char* e = getenv("VLMCLIP_GEMM_DEBUG");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  p.debug = dbg_flag;
+  // stages / panels-per-group of the pair kernel: 52 (default), 43, 61 (VLMCLIP_GEMM_RES2_CFG, for measurements)
+  static const int cfg = []() {
+    const char* e = getenv("VLMCLIP_GEMM_RES2_CFG");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+
+  bool wide = N > 128;
+  if (wide) {
+    const int sms = sm_count();
+    const long t256 = (long)p.m_tiles * ((N + 255) / 256), t128 = (long)p.m_tiles * ((N + 127) / 128);
+    const double c256 = (double)((t256 + sms - 1) / sms), c128 = 0.56 * (double)((t128 + sms - 1) / sms);
+    if (c128 < 0.92 * c256) wide = false;
+  }
+  const bool pair = wide && M > BLOCK_M;
+  CUtensorMap tmA, tmB, tmX;
+  int rc = make_tmap_bf16(&tmA, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, W, N, K, ldw, pair ? 128 : (wide ? 256 : 128));
+  if (rc) return rc;
+  rc = make_tmap_bf16_planes(&tmX, X, M, N, ldx, plane_stride, 2, BLOCK_M, PANEL_N);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  count_launch(1);
+  if (pair) {
+    if (cfg == 43) return launch_gemm<256, 4, 3, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+    if (cfg == 61) return launch_gemm<256, 6, 1, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+    return launch_gemm<256, 5, 2, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+  }
+  if (wide) return launch_gemm<256, 4, 1, false, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+  return launch_gemm<128, 4, 2, false, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
 }

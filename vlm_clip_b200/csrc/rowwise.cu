@@ -31,6 +31,14 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   o.w = pack_bf16x2(f[6], f[7]);
   return o;
 }
+// second term of the two-term (hi + lo) residual stream: bf16(f - hi)
+__device__ __forceinline__ uint4 pack8_lo(const float* f, const uint4& hi) {
+  float h[8], d[8];
+  unpack8(hi, h);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] = f[j] - h[j];
+  return pack8(d);
+}
 
 // mean / rstd of one row held as v[NV][8] per lane
 template <int NV>
@@ -200,8 +208,8 @@ template <int NV, bool PATCH_BF16>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 vision_embed_ln_kernel(const void* __restrict__ patch_v, const float* __restrict__ cls,
                        const float* __restrict__ pos, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int B, int S, int D,
-                       float eps) {
+                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                       __nv_bfloat16* __restrict__ y_lo, int B, int S, int D, float eps) {
   const int64_t row = blockIdx.x * (int64_t)ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= (int64_t)B * S) return;
   const int lane = threadIdx.x & 31;
@@ -256,7 +264,9 @@ vision_embed_ln_kernel(const void* __restrict__ patch_v, const float* __restrict
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gv[j], bv[j]);
-      st_v4(yr + c, pack8(o));
+      const uint4 hi = pack8(o);
+      st_v4(yr + c, hi);
+      if (y_lo != nullptr) st_v4(y_lo + row * D + c, pack8_lo(o, hi));
     }
   }
 }
@@ -264,7 +274,7 @@ vision_embed_ln_kernel(const void* __restrict__ patch_v, const float* __restrict
 template <typename TokT>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 text_embed_kernel(const int64_t* __restrict__ ids, const TokT* __restrict__ tok, const float* __restrict__ pos,
-                  __nv_bfloat16* __restrict__ y, int B, int S, int D, int V) {
+                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_lo, int B, int S, int D, int V) {
   const int64_t row = blockIdx.x * (int64_t)ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= (int64_t)B * S) return;
   const int lane = threadIdx.x & 31;
@@ -277,18 +287,23 @@ text_embed_kernel(const int64_t* __restrict__ ids, const TokT* __restrict__ tok,
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = (float)tr[c + j] + __ldg(pr + c + j);
-    st_v4(y + row * D + c, pack8(o));
+    const uint4 hi = pack8(o);
+    st_v4(y + row * D + c, hi);
+    if (y_lo != nullptr) st_v4(y_lo + row * D + c, pack8_lo(o, hi));
   }
 }
 
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ y, int R, int D) {
+gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo, int64_t ldx,
+                   float* __restrict__ y, int R, int D) {
   const int64_t total = (int64_t)R * D;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / D;
     const int c = (int)(idx - r * D);
-    y[idx] = __bfloat162float(x[r * ldx + c]);
+    float v = __bfloat162float(x[r * ldx + c]);
+    if (x_lo != nullptr) v += __bfloat162float(x_lo[r * ldx + c]);
+    y[idx] = v;
   }
 }
 
@@ -435,49 +450,55 @@ extern "C" int vlmclip_im2col_patches(const void* pixels, int pix_bf16, void* ou
 }
 
 extern "C" int vlmclip_vision_embed_ln(const void* patch, int patch_bf16, const float* cls, const float* pos,
-                                       const float* gamma, const float* beta, void* y, int B, int S, int D, float eps,
-                                       void* stream) {
+                                       const float* gamma, const float* beta, void* y, void* y_lo, int B, int S, int D,
+                                       float eps, void* stream) {
   VLMCLIP_CHECK_ARG(patch && cls && pos && gamma && beta && y, "vision_embed_ln: null pointer");
   VLMCLIP_CHECK_ARG(B > 0 && S > 1 && D % 8 == 0 && D <= MAX_VEC * 256, "vision_embed_ln: bad dims B=%d S=%d D=%d", B, S, D);
   VLMCLIP_CHECK_ARG((uintptr_t)patch % 16 == 0 && (uintptr_t)cls % 16 == 0 && (uintptr_t)pos % 16 == 0 &&
-                        (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0,
+                        (uintptr_t)y % 16 == 0 && (uintptr_t)y_lo % 16 == 0 && (uintptr_t)gamma % 16 == 0 &&
+                        (uintptr_t)beta % 16 == 0,
                     "vision_embed_ln: pointers must be 16-byte aligned");
   const int64_t rows = (int64_t)B * S;
   const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   count_launch(1);
   if (patch_bf16) {
     VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV, true><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
+                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, B, S, D, eps)));
   } else {
     VLMCLIP_DISPATCH_NV(D, (vision_embed_ln_kernel<NV, false><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, B, S, D, eps)));
+                               patch, cls, pos, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, B, S, D, eps)));
   }
   return report_cuda(cudaGetLastError(), "vision_embed_ln_kernel launch");
 }
 
-extern "C" int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y,
+extern "C" int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const float* pos, void* y, void* y_lo,
                                   int B, int S, int D, int V, void* stream) {
   VLMCLIP_CHECK_ARG(ids && tok && pos && y, "text_embed: null pointer");
   VLMCLIP_CHECK_ARG(B > 0 && S > 0 && D % 8 == 0 && V > 0, "text_embed: bad dims");
-  VLMCLIP_CHECK_ARG((uintptr_t)y % 16 == 0, "text_embed: y must be 16-byte aligned");
+  VLMCLIP_CHECK_ARG((uintptr_t)y % 16 == 0 && (uintptr_t)y_lo % 16 == 0, "text_embed: y / y_lo must be 16-byte aligned");
   const int64_t rows = (int64_t)B * S;
   const int grid = (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   count_launch(1);
   if (tok_bf16)
     text_embed_kernel<__nv_bfloat16><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-        ids, (const __nv_bfloat16*)tok, pos, (__nv_bfloat16*)y, B, S, D, V);
+        ids, (const __nv_bfloat16*)tok, pos, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, B, S, D, V);
   else
     text_embed_kernel<float><<<grid, ROWS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-        ids, (const float*)tok, pos, (__nv_bfloat16*)y, B, S, D, V);
+        ids, (const float*)tok, pos, (__nv_bfloat16*)y, (__nv_bfloat16*)y_lo, B, S, D, V);
   return report_cuda(cudaGetLastError(), "text_embed_kernel launch");
 }
 
-extern "C" int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream) {
+extern "C" int vlmclip_gather_rows2_bf16_to_f32(const void* x, const void* x_lo, int64_t ldx, float* y, int R, int D,
+                                                void* stream) {
   VLMCLIP_CHECK_ARG(x && y && R > 0 && D > 0 && ldx >= D, "gather_rows: bad arguments");
   count_launch(1);
-  gather_rows_kernel<<<grid_for((int64_t)R * D, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx,
-                                                                                    y, R, D);
+  gather_rows_kernel<<<grid_for((int64_t)R * D, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)x_lo, ldx, y, R, D);
   return report_cuda(cudaGetLastError(), "gather_rows_kernel launch");
+}
+
+extern "C" int vlmclip_gather_rows_bf16_to_f32(const void* x, int64_t ldx, float* y, int R, int D, void* stream) {
+  return vlmclip_gather_rows2_bf16_to_f32(x, nullptr, ldx, y, R, D, stream);
 }
 
 extern "C" int vlmclip_ln_partials_to_stats(const float* partials, float* stats_out, int M, int npart, float eps,

@@ -195,7 +195,7 @@ class CLIPWithAdapters(nn.Module):
             return self._ft_text_features(input_ids, attention_mask)
         bb = self._backbone()
         input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
-        hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)  # bf16 [B*S, Dt]
+        hidden = bb.text_stream_pre_ln(input_ids, attention_mask)  # [B*S, Dt] stream (towers.Hidden)
         return self._text_head(bb, hidden, input_ids.shape[0], input_ids.shape[1])
 
     def _text_inputs(self, input_ids, attention_mask):
@@ -205,8 +205,9 @@ class CLIPWithAdapters(nn.Module):
         return input_ids, attention_mask
 
     def _text_head(self, bb, hidden, B, S):
-        # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32
-        tok0 = ops.layernorm_rows_f32(hidden, bb.final_ln_w, bb.final_ln_b, bb.eps_t, rows=B, ldx=S * bb.Dt)
+        # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32, read from both terms of
+        # the residual stream
+        tok0 = ops.layernorm_f32(hidden.rows_f32(B, S * bb.Dt, bb.Dt), bb.final_ln_w, bb.final_ln_b, bb.eps_t)
         if self.use_text_adapter:
             tok0 = self.text_adapter(tok0)
         if self.use_shared_adapters:
@@ -243,25 +244,26 @@ class CLIPWithAdapters(nn.Module):
         return ops.mean_pool(self._image_head(bb, hidden, n, seq), T)
 
     def _vision_hidden(self, bb, pixel_values):
-        """Tower output for any accepted pixel layout -> (bf16 [n*seq, D], n images, seq rows per image kept)."""
+        """Tower output for any accepted pixel layout -> (towers.Hidden stream [n*seq, D], n images, seq rows per image kept)."""
         cls_only = self.vision_cls_only_last_layer and bb.fold_ln
         seq = 1 if cls_only else bb.Sv
         if pixel_values.dtype == torch.uint8:
             if pixel_values.dim() not in (4, 5) or pixel_values.shape[-1] != 3:
                 raise ValueError("uint8 frames must be [B, Hs, Ws, 3] or [B, T, Hs, Ws, 3]")
             n = pixel_values.numel() // (pixel_values.shape[-3] * pixel_values.shape[-2] * 3)
-            return bb.vision_hidden_u8(pixel_values, self.pixel_mean, self.pixel_std, self.frames_bgr, cls_only), n, seq
+            return bb.vision_stream_u8(pixel_values, self.pixel_mean, self.pixel_std, self.frames_bgr, cls_only), n, seq
         if pixel_values.dim() == 5:  # [B, 3, T, H, W] -> [B*T, 3, H, W] (a layout copy, as the reference's caller would do)
             B, C, T, H, W = pixel_values.shape
             pixel_values = pixel_values.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
-        return bb.vision_hidden(pixel_values, cls_only), pixel_values.shape[0], seq
+        return bb.vision_stream(pixel_values, cls_only), pixel_values.shape[0], seq
 
     def _image_head(self, bb, hidden, B, seq=None):
         seq = bb.Sv if seq is None else seq
+        # the CLS rows in fp32 (hi + lo of the residual stream); the adapter is position-wise, so evaluating it on row 0
+        # of every sequence is result-identical to the reference's all-token call followed by [:, 0, :] (model_m.py:116-122)
+        cls = hidden.rows_f32(B, seq * bb.Dv, bb.Dv)
         if self.use_vision_adapter:
-            cls = self.vision_adapter.forward_token0(hidden, B, seq)
-        else:
-            cls = ops.gather_rows_f32(hidden, B, seq * bb.Dv, bb.Dv)
+            cls = self.vision_adapter(cls)
         return ops.linear_f32(cls, bb.visual_projection)
 
     def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True, *, inputs_ready=None):
@@ -327,7 +329,7 @@ class CLIPWithAdapters(nn.Module):
                 st.wait_stream(main)
         input_ids, attention_mask = self._text_inputs(input_ids, attention_mask)
         with torch.cuda.stream(txt):
-            t_hidden = bb.text_hidden_pre_ln(input_ids, attention_mask)
+            t_hidden = bb.text_stream_pre_ln(input_ids, attention_mask)
         with torch.cuda.stream(vis):
             v_hidden, n_img, v_seq = self._vision_hidden(bb, pixel_values)
         input_ids.record_stream(txt)

@@ -83,6 +83,30 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
 
 
 @_traced
+def gemm_res2(a, w, bias, x2, stats_part_out=None):
+    """Two-term residual update in place (vlmclip_gemm_bf16_res2): x2[0] + x2[1] += a[M,K] @ w[N,K]^T + bias, with
+    x2 = bf16 [2, M, N] holding hi = bf16(x) and lo = bf16(x - hi).  Returns x2."""
+    _req(a.dtype == bf16 and w.dtype == bf16 and x2.dtype == bf16, "gemm_res2: a, w, x2 must be bf16")
+    _req(a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1,
+         "gemm_res2: operands must be row-major [M, K] / [N, K]")
+    M, K = a.shape
+    Nn = w.shape[0]
+    _req(x2.dim() == 3 and x2.shape == (2, M, Nn) and x2.stride(2) == 1, "gemm_res2: x2 must be [2, M, N]")
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    N.check(
+        N.load().vlmclip_gemm_bf16_res2(N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(x2), x2.stride(1), x2.stride(0),
+                                        N.ptr(bias), N.ptr(stats_part_out), M, Nn, K, N.stream()),
+        "vlmclip_gemm_bf16_res2")
+    if prof is not None:
+        e1.record()
+        prof["gemm"].append((e0, e1, 2.0 * M * Nn * K))
+    return x2
+
+
+@_traced
 def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm: x must be bf16 [M, D]")
     M, D = x.shape
@@ -225,7 +249,8 @@ def mean_pool(x, T: int):
 
 
 @_traced
-def vision_embed_ln(patch, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None):
+def vision_embed_ln(patch, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=None, out_lo=None):
+    """`out_lo` (optional, bf16 [B*S, D]): second term of the two-term residual stream, bf16(value - out)."""
     D = pos.shape[1]
     _req(patch.dtype in (f32, bf16) and patch.shape == (B * (S - 1), D) and patch.is_contiguous(),
          "vision_embed_ln: patch must be fp32 or bf16 [B*(S-1), D]")
@@ -233,12 +258,12 @@ def vision_embed_ln(patch, cls, pos, gamma, beta, B: int, S: int, eps=1e-5, out=
         out = torch.empty((B * S, D), device=pos.device, dtype=bf16)
     N.check(
         N.load().vlmclip_vision_embed_ln(N.ptr(patch), 1 if patch.dtype == bf16 else 0, N.ptr(cls), N.ptr(pos), N.ptr(gamma), N.ptr(beta),
-                                         N.ptr(out), B, S, D, float(eps), N.stream()), "vlmclip_vision_embed_ln")
+                                         N.ptr(out), N.ptr(out_lo), B, S, D, float(eps), N.stream()), "vlmclip_vision_embed_ln")
     return out
 
 
 @_traced
-def text_embed(ids, tok, pos, out=None):
+def text_embed(ids, tok, pos, out=None, out_lo=None):
     _req(ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous(), "text_embed: ids must be int64 [B,S]")
     B, S = ids.shape
     V, D = tok.shape
@@ -246,8 +271,8 @@ def text_embed(ids, tok, pos, out=None):
     if out is None:
         out = torch.empty((B * S, D), device=ids.device, dtype=bf16)
     N.check(
-        N.load().vlmclip_text_embed(N.ptr(ids), N.ptr(tok), 1 if tok.dtype == bf16 else 0, N.ptr(pos), N.ptr(out), B,
-                                    S, D, V, N.stream()), "vlmclip_text_embed")
+        N.load().vlmclip_text_embed(N.ptr(ids), N.ptr(tok), 1 if tok.dtype == bf16 else 0, N.ptr(pos), N.ptr(out),
+                                    N.ptr(out_lo), B, S, D, V, N.stream()), "vlmclip_text_embed")
     return out
 
 
@@ -286,11 +311,24 @@ def attention_1q(q, k, v, S: int, H: int, kv_row_stride: int, kv_batch_stride: i
 
 
 @_traced
-def gather_rows_f32(x, rows: int, ld: int, D: int):
-    """y[r] = float(x.flat[r*ld : r*ld + D]) — the token-0 slice of a [B*S, D] bf16 activation."""
+def gather_rows_f32(x, rows: int, ld: int, D: int, lo=None):
+    """y[r] = float(x.flat[r*ld : r*ld + D]) (+ float(lo.flat[...]) for a two-term stream) — the token-0 slice of a
+    [B*S, D] bf16 activation."""
     out = torch.empty((rows, D), device=x.device, dtype=f32)
-    N.check(N.load().vlmclip_gather_rows_bf16_to_f32(N.ptr(x), ld, N.ptr(out), rows, D, N.stream()),
-            "vlmclip_gather_rows_bf16_to_f32")
+    N.check(N.load().vlmclip_gather_rows2_bf16_to_f32(N.ptr(x), N.ptr(lo), ld, N.ptr(out), rows, D, N.stream()),
+            "vlmclip_gather_rows2_bf16_to_f32")
+    return out
+
+
+@_traced
+def layernorm_f32(x, gamma, beta, eps=1e-5):
+    """fp32 LayerNorm of fp32 rows [R, D] (forward only: the frozen towers' final / post LayerNorm on pooled rows)."""
+    _req(x.dtype == f32 and x.dim() == 2 and x.stride(1) == 1, "layernorm_f32: x must be fp32 [R, D]")
+    R, D = x.shape
+    out = torch.empty((R, D), device=x.device, dtype=f32)
+    stats = torch.empty((R, 2), device=x.device, dtype=f32)
+    N.check(N.load().vlmclip_layernorm_f32(N.ptr(x), x.stride(0), N.ptr(gamma), N.ptr(beta), N.ptr(out), N.ptr(stats), R, D,
+                                           float(eps), N.stream()), "vlmclip_layernorm_f32")
     return out
 
 

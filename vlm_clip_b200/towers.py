@@ -89,11 +89,39 @@ def _pack_layers(sd: Dict[str, torch.Tensor], prefix: str, dev, keep_raw: bool) 
 _STATS_IN_GEMM = os.environ.get("VLMCLIP_STATS_IN_GEMM", "0") == "1"  # experiment switch
 
 
+class Hidden:
+    """A tower's output stream [B*S, D].  `hi` is the bf16 tensor every bf16 consumer reads; with the two-term residual
+    stream (`NativeClipTowers(residual="hilo")`, the default) `lo` holds bf16(x - hi) and fp32 consumers (the pooled
+    rows that feed adapters / projections) read hi + lo."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: Optional[torch.Tensor] = None):
+        self.hi, self.lo = hi, lo
+
+    def rows_f32(self, rows: int, ld: int, D: int) -> torch.Tensor:
+        """fp32 [rows, D]: row r = elements [r*ld, r*ld + D) of the stream (token 0 of every sequence for ld = S*D)."""
+        return ops.gather_rows_f32(self.hi, rows, ld, D, lo=self.lo)
+
+    def record_stream(self, stream) -> None:
+        self.hi.record_stream(stream)
+        if self.lo is not None:
+            self.lo.record_stream(stream)
+
+
 class NativeClipTowers:
     """Device-resident packed weights + forward of both frozen towers."""
 
-    def __init__(self, clip, device=None, fold_ln: bool = True, keep_raw: bool = False):
+    def __init__(self, clip, device=None, fold_ln: bool = True, keep_raw: bool = False, residual: Optional[str] = None):
+        """residual: "hilo" (default; VLMCLIP_RESIDUAL overrides) keeps the residual stream as two bf16 planes hi + lo
+        (vlmclip_gemm_bf16_res2) so that its 2 x L in-place updates do not accumulate bf16 rounding; "bf16" keeps one
+        plane (less HBM traffic, ~2.5x the end-to-end error: oracle/emulate_bf16.py).  LN folding is required for
+        "hilo" (the unfolded path exists to bound the fold's error in tests)."""
         N.load()
+        residual = residual or os.environ.get("VLMCLIP_RESIDUAL", "hilo")
+        if residual not in ("hilo", "bf16"):
+            raise ValueError(f"residual must be 'hilo' or 'bf16', got {residual!r}")
+        self.residual = residual if fold_ln else "bf16"
         dev = torch.device(device) if device is not None else next(clip.parameters()).device
         if dev.type != "cuda":
             raise N.NativeError("NativeClipTowers needs a CUDA device: the towers only run on the sm_100a library")
@@ -154,11 +182,18 @@ class NativeClipTowers:
             self._tables[key] = tab
         return tab
 
-    def _encoder(self, x: torch.Tensor, layers: List[_Layer], B: int, S: int, H: int, eps: float, causal: bool,
-                 key_mask: Optional[torch.Tensor], cls_only: bool = False) -> torch.Tensor:
-        """All encoder layers over the residual stream x [B*S, D] (in place).  `cls_only` (vision, LN folded): the last
-        layer is evaluated for token 0 of every sequence only and [B, D] is returned (see `_last_layer_cls`)."""
-        M, D = x.shape
+    def _new_stream(self, M: int, D: int, dev) -> torch.Tensor:
+        """Storage of a residual stream: bf16 [P, M, D] with P = 2 planes (hi, lo) for the two-term stream, else 1."""
+        return torch.empty((2 if self.residual == "hilo" else 1, M, D), device=dev, dtype=bf16)
+
+    def _encoder(self, x2: torch.Tensor, layers: List[_Layer], B: int, S: int, H: int, eps: float, causal: bool,
+                 key_mask: Optional[torch.Tensor], cls_only: bool = False) -> Hidden:
+        """All encoder layers over the residual stream x2 [P, B*S, D] (in place; see `_new_stream`).  `cls_only` (vision,
+        LN folded): the last layer is evaluated for token 0 of every sequence only and [B, D] is returned (see
+        `_last_layer_cls`)."""
+        P, M, D = x2.shape
+        x = x2[0]
+        x_lo = x2[1] if P == 2 else None
         F = layers[0].fc1_w.shape[0]
         dev = x.device
         qkv = torch.empty((M, 3 * D), device=dev, dtype=bf16)
@@ -178,12 +213,21 @@ class NativeClipTowers:
             if n_full > 0:
                 table = self._layer_table(layers)
                 N.check(
-                    N.load().vlmclip_encoder_fwd(table, n_full, N.ptr(x), N.ptr(qkv), N.ptr(att), N.ptr(hid), N.ptr(stats),
-                                                 N.ptr(part), N.ptr(key_mask), B, S, H, D, F, float(eps),
+                    N.load().vlmclip_encoder_fwd(table, n_full, N.ptr(x), N.ptr(x_lo), N.ptr(qkv), N.ptr(att), N.ptr(hid),
+                                                 N.ptr(stats), N.ptr(part), N.ptr(key_mask), B, S, H, D, F, float(eps),
                                                  1 if causal else 0, N.ACT_QUICK_GELU, N.stream()), "vlmclip_encoder_fwd")
             if cls_only:
-                return self._last_layer_cls(x, layers[-1], B, S, H, eps, qkv, stats, part, first=n_full == 0)
-            return x
+                return Hidden(self._last_layer_cls(x, L=layers[-1], B=B, S=S, H=H, eps=eps, qkv=qkv, stats=stats, part=part,
+                                                   first=n_full == 0))
+            return Hidden(x, x_lo)
+
+        def residual_gemm(a, w, b):
+            # x += a w^T + b: the same thread reads and writes each element, so the update is done in place
+            if x_lo is not None:
+                ops.gemm_res2(a, w, b, x2, stats_part_out=part)
+            else:
+                ops.gemm(a, w, bias=b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
+
         first = True
         for L in layers:
             if self.fold_ln:
@@ -200,8 +244,7 @@ class NativeClipTowers:
                 ops.layernorm(x, L.ln1_w, L.ln1_b, eps, out=xn)
                 ops.gemm(xn, L.qkv_w_raw, bias=L.qkv_b_raw, out=qkv)
             ops.attention(qkv, B, S, H, causal=causal, key_mask=key_mask, out=att)
-            # x += out_proj(att): the same thread reads and writes each element, so the update is done in place
-            ops.gemm(att, L.out_w, bias=L.out_b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
+            residual_gemm(att, L.out_w, L.out_b)
             if self.fold_ln and _STATS_IN_GEMM:
                 ops.gemm(x, L.fc1_w, bias=L.fc1_b, stats_part_in=part, ln_eps=eps, col_c=L.fc1_c, act=N.ACT_QUICK_GELU,
                          out=hid)
@@ -211,8 +254,8 @@ class NativeClipTowers:
             else:
                 ops.layernorm(x, L.ln2_w, L.ln2_b, eps, out=xn)
                 ops.gemm(xn, L.fc1_w_raw, bias=L.fc1_b_raw, act=N.ACT_QUICK_GELU, out=hid)
-            ops.gemm(hid, L.fc2_w, bias=L.fc2_b, residual=x, out=x, stats_part_out=part if self.fold_ln else None)
-        return x
+            residual_gemm(hid, L.fc2_w, L.fc2_b)
+        return Hidden(x, x_lo)
 
     def _last_layer_cls(self, x, L: _Layer, B: int, S: int, H: int, eps: float, qkv, stats, part, first: bool):
         """Last encoder layer for token 0 only -> bf16 [B, D] = last_hidden_state[:, 0].
@@ -236,9 +279,9 @@ class NativeClipTowers:
 
     # ------------------------------------------------------------------------------------------ towers
     @torch.no_grad()
-    def vision_hidden(self, pixel_values: torch.Tensor, cls_only: bool = False) -> torch.Tensor:
-        """`vision_model(pixel_values).last_hidden_state` as bf16 [B*S, D] (NOT through post_layernorm, HF:684);
-        with `cls_only` just its token-0 rows, bf16 [B, D]."""
+    def vision_stream(self, pixel_values: torch.Tensor, cls_only: bool = False) -> Hidden:
+        """`vision_model(pixel_values).last_hidden_state` (NOT through post_layernorm, HF:684) as a `Hidden` stream
+        [B*S, D]; with `cls_only` just its token-0 rows, [B, D]."""
         if pixel_values.dim() != 4 or pixel_values.shape[1] != 3:
             raise ValueError("pixel_values must be [B, 3, H, W]")
         if pixel_values.shape[2] != self.image or pixel_values.shape[3] != self.image:
@@ -250,14 +293,20 @@ class NativeClipTowers:
         B = pixel_values.shape[0]
         return self._vision_from_cols(ops.im2col(pixel_values, self.patch), B, cls_only)
 
-    def _vision_from_cols(self, cols: torch.Tensor, B: int, cls_only: bool = False) -> torch.Tensor:
+    def vision_hidden(self, pixel_values: torch.Tensor, cls_only: bool = False) -> torch.Tensor:
+        """bf16 view of `vision_stream` (the hi plane)."""
+        return self.vision_stream(pixel_values, cls_only).hi
+
+    def _vision_from_cols(self, cols: torch.Tensor, B: int, cls_only: bool = False) -> Hidden:
         patches = ops.gemm(cols, self.patch_w)  # [B*np, D] bf16 (staged TMA epilogue; the fp32 path costs 2x the traffic)
-        x = ops.vision_embed_ln(patches, self.cls, self.pos_v, self.pre_ln_w, self.pre_ln_b, B, self.Sv, self.eps_v)
-        return self._encoder(x, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None, cls_only)
+        x2 = self._new_stream(B * self.Sv, self.Dv, cols.device)
+        ops.vision_embed_ln(patches, self.cls, self.pos_v, self.pre_ln_w, self.pre_ln_b, B, self.Sv, self.eps_v, out=x2[0],
+                            out_lo=x2[1] if x2.shape[0] == 2 else None)
+        return self._encoder(x2, self.v_layers, B, self.Sv, self.Hv, self.eps_v, False, None, cls_only)
 
     @torch.no_grad()
-    def vision_hidden_u8(self, frames_u8: torch.Tensor, mean, std, bgr: bool = False, cls_only: bool = False) -> torch.Tensor:
-        """Same as `vision_hidden`, from decoded uint8 frames [..., Hs, Ws, 3]: resize to the model resolution, /255 and
+    def vision_stream_u8(self, frames_u8: torch.Tensor, mean, std, bgr: bool = False, cls_only: bool = False) -> Hidden:
+        """Same as `vision_stream`, from decoded uint8 frames [..., Hs, Ws, 3]: resize to the model resolution, /255 and
         normalisation are fused into the patch extraction (process_video.py:14-29 semantics; `vlmclip_preprocess_patches`)."""
         if frames_u8.dtype != torch.uint8 or frames_u8.dim() < 4 or frames_u8.shape[-1] != 3:
             raise ValueError("frames must be uint8 [..., Hs, Ws, 3]")
@@ -266,9 +315,12 @@ class NativeClipTowers:
         cols = ops.preprocess_patches(frames_u8, self.image, self.image, self.patch, mean, std, bgr)
         return self._vision_from_cols(cols, n, cls_only)
 
+    def vision_hidden_u8(self, frames_u8, mean, std, bgr: bool = False, cls_only: bool = False) -> torch.Tensor:
+        return self.vision_stream_u8(frames_u8, mean, std, bgr, cls_only).hi
+
     @torch.no_grad()
-    def text_hidden_pre_ln(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """Text encoder output BEFORE final_layer_norm, bf16 [B*S, D]."""
+    def text_stream_pre_ln(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> Hidden:
+        """Text encoder output BEFORE final_layer_norm, `Hidden` stream [B*S, D]."""
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, S]")
         B, S = input_ids.shape
@@ -279,8 +331,12 @@ class NativeClipTowers:
         key_mask = None
         if attention_mask is not None:
             key_mask = (attention_mask != 0).to(torch.uint8).contiguous()
-        x = ops.text_embed(ids, self.tok, self.pos_t)
-        return self._encoder(x, self.t_layers, B, S, self.Ht, self.eps_t, True, key_mask)
+        x2 = self._new_stream(B * S, self.Dt, ids.device)
+        ops.text_embed(ids, self.tok, self.pos_t, out=x2[0], out_lo=x2[1] if x2.shape[0] == 2 else None)
+        return self._encoder(x2, self.t_layers, B, S, self.Ht, self.eps_t, True, key_mask)
+
+    def text_hidden_pre_ln(self, input_ids, attention_mask) -> torch.Tensor:
+        return self.text_stream_pre_ln(input_ids, attention_mask).hi
 
     @torch.no_grad()
     def text_hidden(self, input_ids, attention_mask) -> torch.Tensor:
@@ -292,22 +348,24 @@ class NativeClipTowers:
     @torch.no_grad()
     def image_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
         """CLIPModel.get_image_features (HF:829-863): projection(post_layernorm(CLS)), fp32 [B, P]."""
-        x = self.vision_hidden(pixel_values)
+        h = self.vision_stream(pixel_values)
         B = pixel_values.shape[0]
-        pooled = ops.layernorm_rows_f32(x, self.post_ln_w, self.post_ln_b, self.eps_v, rows=B, ldx=self.Sv * self.Dv)
+        cls = h.rows_f32(B, self.Sv * self.Dv, self.Dv)
+        pooled = ops.layernorm_f32(cls, self.post_ln_w, self.post_ln_b, self.eps_v)
         return ops.linear_f32(pooled, self.visual_projection)
 
     @torch.no_grad()
     def text_features(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
         """CLIPModel.get_text_features (HF:793-827): projection of the final-LN state at the EOS position."""
-        x = self.text_hidden_pre_ln(input_ids, attention_mask)
+        h = self.text_stream_pre_ln(input_ids, attention_mask)
         B, S = input_ids.shape
         ids = input_ids.to(torch.int)
         if self.eos_token_id == 2:
             eos = ids.argmax(dim=-1)  # HF:564-575 (index bookkeeping on [B,S] ints, not arithmetic on activations)
         else:
             eos = (ids == self.eos_token_id).int().argmax(dim=-1)
-        rows = (torch.arange(B, device=x.device) * S + eos).to(torch.int64)
-        picked = x.index_select(0, rows).contiguous()
-        pooled = ops.layernorm_rows_f32(picked, self.final_ln_w, self.final_ln_b, self.eps_t, rows=B, ldx=self.Dt)
+        rows = (torch.arange(B, device=h.hi.device) * S + eos).to(torch.int64)
+        picked = Hidden(h.hi.index_select(0, rows).contiguous(),
+                        None if h.lo is None else h.lo.index_select(0, rows).contiguous())
+        pooled = ops.layernorm_f32(picked.rows_f32(B, self.Dt, self.Dt), self.final_ln_w, self.final_ln_b, self.eps_t)
         return ops.linear_f32(pooled, self.text_projection)
