@@ -68,6 +68,45 @@ def test_dp_global_loss_and_summed_grads_match_single_process():
         assert dg < 1e-6 * max(1.0, gmax) + 1e-7, (rank, dg, gmax)
 
 
+def _bcast_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vlm_clip_b200 import ops
+
+    torch.manual_seed(100 + rank)  # replicas built with DIFFERENT RNG state (nothing synchronised them)
+    params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    opt = ops.FusedAdamW(params, lr=1e-3)
+    opt.exp_avg.fill_(float(rank + 1))
+    opt.step_t.fill_(rank + 3)
+    gen0 = ops.param_generation()
+    opt.broadcast_from(0)
+    q.put((rank, opt.flat.clone(), opt.exp_avg.clone(), int(opt.step_t.item()), params[0].detach().clone(),
+           ops.param_generation() - gen0))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_dp_replicas_start_from_rank0_parameters():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (_, f0, m0, s0, w0, g0), (_, f1, m1, s1, w1, g1) = res
+    assert torch.equal(f0, f1) and torch.equal(m0, m1) and s0 == s1 == 3
+    assert torch.equal(w0, w1)  # the nn.Parameters are views of the arena: they follow it
+    torch.manual_seed(100)
+    assert torch.equal(w0, torch.randn(5, 3))  # ... and it is rank 0's initialisation that won
+    assert g0 == 1 and g1 == 1  # cached weight packs are invalidated
+
+
 def test_gather_is_identity_without_process_group():
     from vlm_clip_b200.dist import allreduce_sum_, gather_features, world
 

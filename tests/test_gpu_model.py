@@ -2,15 +2,16 @@
 same seeded weights and inputs.
 
 Tolerances.  BASELINE.json's north_star asks for bf16 logits within 1e-2 relative, fp32 loss within 1e-4 and
-identical argmax.  The loss kernel itself meets 1e-4 on equal features (test_loss_kernel_on_oracle_features,
-tests/test_gpu_kernels.py::test_clip_loss).  End to end, the 12-layer bf16 backbone (bf16 residual stream) sits at
-~9e-3 relative on the hidden states against the fp32 oracle (torch's own bf16 autocast of the same model: ~4e-3,
-measured by tools/kernel_bench.py), and with RANDOM-INIT weights the image/text features are nearly orthogonal
-(|cos| ~ 0.03), so a 1e-2 feature error shows up as 2-3e-2 relative on the (tiny) logits.  The bounds below are the
-measured values with ~1.5x margin; argmax identity and the 1e-4 loss bound on equal features are kept strict."""
-FEAT_TOL = 2e-2     # pooled features / hidden states, relative L2
-LOGIT_TOL = 5e-2    # logits of near-orthogonal random-init features, relative L2
-LOSS_TOL = 4e-3     # end-to-end loss through the bf16 backbone, absolute
+identical argmax; tests/test_gpu_parity_fullsize.py holds exactly those numbers at the BASELINE configs (ViT-B/16 with
+256 pairs: logits 7.0e-3, loss 1.2e-5; ViT-L/14 at full depth) next to torch's own bf16 autocast as a yardstick.  The
+tests in THIS file run ViT-B/32 with 4-8 pairs, where the same feature error (2e-3 image / 6e-3 text, the floor set by
+the bf16 operand roundings, oracle/emulate_bf16.py; the residual stream is two-term and no longer adds to it) is averaged
+over fewer rows and spread over fewer, smaller logits (random-init features are nearly orthogonal, |cos| ~ 0.03).  The
+bounds below are those small-batch values with ~1.5x margin; the loss kernel itself meets 1e-4 on equal features
+(test_loss_kernel_on_oracle_features, tests/test_gpu_kernels.py::test_clip_loss)."""
+FEAT_TOL = 1e-2     # pooled features / hidden states, relative L2
+LOGIT_TOL = 2e-2    # logits of 4-8 near-orthogonal random-init pairs, relative L2
+LOSS_TOL = 5e-4     # end-to-end loss through the bf16 towers at the random-init logit scale, absolute
 import math
 
 import pytest
@@ -410,6 +411,80 @@ def test_shared_mhs_adapter_training(cuda, clip_b32):
             cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), gr.flatten(), dim=0).item()
             assert cos > 0.97, (k, cos)
     assert all(p_.grad is None for p_ in model.clip.parameters())
+
+
+def test_eval_after_optimizer_steps_sees_updated_weights(cuda, clip_b32):
+    """the bf16 weight packs of the inference paths were keyed on Parameter._version only, which
+    FusedAdamW (raw-pointer updates of the arena) never moves, so `evaluate()` after an epoch ran the first epoch's
+    matrices.  eval -> N optimiser steps -> eval must follow the fp32 trainable path evaluated on the new weights."""
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    torch.manual_seed(2)
+    model = CLIPWithAdapters(clip=clip_b32, use_shared_adapters=True, shared_adapter_layers=1).to(cuda)
+    for ad in model.shared_adapters:  # deterministic trainable path for the comparison
+        ad.cross_attn.dropout = 0.0
+        ad.mlp[3].p = 0.0
+    pix, ids, mask = O.synthetic_batch(4, seed=8)
+    ids[:, 0] = torch.arange(4) * 13 + 2
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    model.eval()
+    with torch.no_grad():
+        t_before = model.get_text_features(ids, mask).clone()  # packs the bf16 copies
+    trainer = CLIPAdapterTrainer(model, [None], learning_rate=3e-3, output_dir="/tmp/vlmclip_test_stale")
+    model.train()
+    for _ in range(4):
+        trainer.training_step({"input_ids": ids, "attention_mask": mask, "pixel_values": pix})
+    model.eval()
+    with torch.no_grad():
+        t_after = model.get_text_features(ids, mask)     # bf16 inference path, must re-pack
+    model.train()
+    t_ref = model.get_text_features(ids, mask).detach()  # fp32 trainable path on the live parameters
+    assert _rel(t_before, t_ref) > 5e-2                  # the steps moved the function ...
+    assert _rel(t_after, t_ref) < 2e-2, (_rel(t_after, t_ref), _rel(t_before, t_ref))  # ... and eval follows it
+
+
+def test_resume_continues_like_an_uninterrupted_run(cuda, clip_b32, tmp_path):
+    """SURVEY.md 8f-4 (the reference has no resume, trainer.py:157-167): 6 steps in one go == 3 steps, save, fresh
+    trainer + model, load, 3 more steps.  Compares parameters, both Adam moments, the step counter and the position in
+    the warm-up / decay schedule."""
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    def batches():
+        out = []
+        for s in range(3):
+            pix, ids, mask = O.synthetic_batch(4, seed=20 + s)
+            ids[:, 0] = torch.arange(4) * 7 + s
+            out.append({"input_ids": ids, "attention_mask": mask, "pixel_values": pix})
+        return out
+
+    def fresh():
+        m = _make_model(cuda, clip_b32, seed=9)
+        return m, CLIPAdapterTrainer(m, batches(), learning_rate=1e-3, warmup_steps=2, output_dir=str(tmp_path / "ck"),
+                                     log_every=1000)
+
+    m_a, tr_a = fresh()
+    tr_a.train(num_epochs=2, save_every=100, eval_every=100)      # 6 steps, uninterrupted
+    m_b, tr_b = fresh()                                            # the interrupted run: 3 steps of the 2-epoch schedule
+    tr_b._total_steps = 6
+    tr_b.optimizer.set_lr(0.0)                                     # step 0 of a 2-step warm-up
+    m_b.train()
+    for b in batches():
+        tr_b.training_step(b)
+    state = str(tmp_path / "state.pt")
+    tr_b.save_training_state(state)
+    assert tr_b._global_step == 3
+    m_c, tr_c = fresh()                                            # new process: fresh model + trainer
+    for p_ in tr_c.trainable_params:
+        p_.data.add_(1.0)                                          # make sure the parameters come from the file
+    tr_c.load_training_state(state)
+    tr_c.train(num_epochs=2, save_every=100, eval_every=100)      # skips the 3 completed steps, runs 3
+    assert tr_c._global_step == 6 == tr_a._global_step
+    assert int(tr_c.optimizer.step_t.item()) == 6
+    for name in ("flat", "exp_avg", "exp_avg_sq"):
+        a, c = getattr(tr_a.optimizer, name), getattr(tr_c.optimizer, name)
+        assert torch.equal(a, c), (name, (a - c).abs().max().item())
+    assert tr_a.optimizer.param_groups[0]["lr"] == tr_c.optimizer.param_groups[0]["lr"]
 
 
 def test_full_size_properties_vit_b16_batch256(cuda):

@@ -109,11 +109,13 @@ def test_parity_vit_b16_batch256_full_depth(cuda, scale):
     # as accurate as torch's own bf16 execution of the model (10 % slack for the different rounding points)
     assert mine["img"] <= 1.1 * base["img"] + 1e-4 and mine["txt"] <= 1.1 * base["txt"] + 1e-4, (mine, base)
     assert mine["logits_l2"] <= 1.1 * base["logits_l2"] + 1e-4, (mine, base)
-    # absolute: features well inside the 1e-2 the north star allows bf16; logits of random-init (near-orthogonal)
-    # features at ~1e-2 of the matrix norm (module docstring)
-    assert mine["img"] < 5e-3 and mine["txt"] < 9e-3, mine
-    assert mine["logits_l2"] < 1.5e-2, mine
-    assert mine["loss"] < (6e-4 if scale is None else 6e-3), mine
+    # absolute, the north star's numbers.  Measured on B200 (round 2): features 2.0e-3 / 6.3e-3, logits 7.0e-3 of the matrix
+    # norm and 8.4e-3 of its largest element, loss 1.2e-5 at the random-init scale and 3.9e-4 at scale 100 (the same
+    # logit error times a 7x larger scale; torch's bf16 autocast: 1.3e-3) - see the module docstring for why 1e-4 at
+    # scale 100 is out of reach of ANY bf16 execution of the towers.
+    assert mine["img"] < 3e-3 and mine["txt"] < 8e-3, mine
+    assert mine["logits_l2"] < 1e-2 and mine["logits_max"] < 1e-2, mine
+    assert mine["loss"] < (1e-4 if scale is None else 1e-3), mine
     assert mine["argmax_i"] >= base["argmax_i"] - 0.02 and mine["argmax_t"] >= base["argmax_t"] - 0.02
 
 
@@ -121,9 +123,10 @@ def test_parity_vit_l14_full_depth(cuda):
     """ViT-L/14 at full depth (24 vision + 12 text layers, S = 257 attention), PE-CLIP adapters, 32 pairs."""
     mine, base = _run_case(cuda, L14, 12, 16, 32, "peclip", None, chunk=16)
     assert mine["img"] <= 1.1 * base["img"] + 1e-4 and mine["txt"] <= 1.1 * base["txt"] + 1e-4, (mine, base)
-    assert mine["img"] < 7e-3 and mine["txt"] < 9e-3, mine
-    assert mine["logits_l2"] < 2e-2, mine
-    assert mine["loss"] < 6e-4, mine
+    # measured: 1.9e-3 / 6.7e-3, logits 8.1e-3, loss 1.3e-4 (32 rows: the mean over rows averages less than at 256)
+    assert mine["img"] < 3e-3 and mine["txt"] < 8e-3, mine
+    assert mine["logits_l2"] < 1e-2, mine
+    assert mine["loss"] < 3e-4, mine
 
 
 def test_two_term_residual_beats_bf16_stream(cuda):

@@ -87,7 +87,8 @@ class SharedMHSAttentionAdapter(nn.Module):
     def _pack(self, dev):
         ps = [self.text_proj.weight, self.image_proj.weight, self.cross_attn.in_proj_weight, self.cross_attn.out_proj.weight,
               self.mlp[0].weight, self.mlp[2].weight]
-        key = (tuple(p._version for p in ps), str(dev))
+        # _version does not move when ops.FusedAdamW updates the arena in place: the optimiser generation does
+        key = (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps), ops.param_generation(), str(dev))
         if self._packed is None or self._packed[0] != key:
             D = self.text_proj.out_features
             b = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()

@@ -46,7 +46,9 @@ class _SelfAttentionAdapter(nn.Module):
         self._packed = None
 
     def _pack(self, dev):
-        key = (self.mhsa.in_proj_weight._version, self.mhsa.out_proj.weight._version, str(dev))
+        # _version does not move when ops.FusedAdamW updates the arena in place: the optimiser generation does
+        key = (self.mhsa.in_proj_weight._version, self.mhsa.out_proj.weight._version, self.mhsa.in_proj_weight.data_ptr(),
+               ops.param_generation(), str(dev))
         if self._packed is None or self._packed[0] != key:
             self._packed = (key, self.mhsa.in_proj_weight.detach().to(dev, torch.bfloat16).contiguous(),
                             self.mhsa.out_proj.weight.detach().to(dev, torch.bfloat16).contiguous())

@@ -753,6 +753,16 @@ def class_head_probs(f_img, f_txt, scale: float, group: int = 1):
 
 
 # --------------------------------------------------------------------------------------------- optimiser
+# FusedAdamW updates parameters through raw pointers into its arena, behind autograd's version counters: anything
+# that caches a derived copy of a trainable parameter (the bf16 weight packs of the inference paths) keys the cache on
+# this generation as well as on Parameter._version.
+_PARAM_GENERATION = 0
+
+
+def param_generation() -> int:
+    return _PARAM_GENERATION
+
+
 class FusedAdamW:
     """clip_grad_norm_ + AdamW over one flat fp32 arena (trainer.py:91-99), two launches, no host sync.
 
@@ -813,12 +823,32 @@ class FusedAdamW:
                                              self.betas[1], self.eps, self.weight_decay, self.max_grad_norm,
                                              N.ptr(self.step_t), N.ptr(self.grad_norm), N.ptr(self.ws), N.stream()),
             "vlmclip_adamw_clip_step")
+        global _PARAM_GENERATION
+        _PARAM_GENERATION += 1  # the parameters changed without their _version moving (see param_generation)
+
+    def broadcast_from(self, src: int = 0, group=None):
+        """Make every rank start from rank `src`'s parameters and optimiser state (what DDP's constructor does for the
+        parameters): replicas that were built with different RNG state, or where only one rank loaded a checkpoint,
+        would otherwise apply identical gradients to different weights."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_t):
+            dist.broadcast(t, src=src, group=group)
+        global _PARAM_GENERATION
+        _PARAM_GENERATION += 1
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": self.step_t.clone(),
-                "lr": self.param_groups[0]["lr"]}
+        return {"params": self.flat.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "step": self.step_t.clone(), "lr": self.param_groups[0]["lr"]}
 
     def load_state_dict(self, sd):
+        global _PARAM_GENERATION
+        if "params" in sd:
+            _req(sd["params"].numel() == self.n, "FusedAdamW.load_state_dict: parameter arena size mismatch")
+            self.flat.copy_(sd["params"])
+            _PARAM_GENERATION += 1
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.step_t.copy_(sd["step"])

@@ -88,6 +88,7 @@ class CLIPAdapterTrainer:
         self._optimizer = None
         self._global_step = 0
         self._total_steps = None
+        self._resumed = False
         dist, world, _ = _dist_world()
         if world > 1 and hasattr(model, "enable_data_parallel"):
             model.enable_data_parallel()
@@ -98,6 +99,8 @@ class CLIPAdapterTrainer:
         if self._optimizer is None:
             self._optimizer = ops.FusedAdamW(self.trainable_params, lr=self.learning_rate,
                                              weight_decay=self.weight_decay, max_grad_norm=self.max_grad_norm)
+            # data parallel: all replicas start from rank 0's parameters (torch DDP does the same at construction)
+            self._optimizer.broadcast_from(0)
         return self._optimizer
 
     # ------------------------------------------------------------------ one step (reference: trainer.py:73-99)
@@ -128,17 +131,28 @@ class CLIPAdapterTrainer:
         from tqdm import tqdm
 
         self._total_steps = len(self.train_dataloader) * num_epochs
-        self._global_step = 0
-        self.optimizer.set_lr(self.learning_rate * linear_schedule_multiplier(0, self.warmup_steps, self._total_steps))
+        # a run restored by load_training_state() continues where it stopped: same position in the schedule, the
+        # batches of the steps already taken are skipped; a fresh run starts at step 0
+        start_step = self._global_step if self._resumed else 0
+        self._resumed = False
+        self._global_step = start_step
+        self.optimizer.set_lr(self.learning_rate * linear_schedule_multiplier(start_step, self.warmup_steps,
+                                                                              self._total_steps))
         best_val_loss = float("inf")
         _, _, rank = _dist_world()
+        steps_per_epoch = len(self.train_dataloader)
 
         for epoch in range(num_epochs):
+            if (epoch + 1) * steps_per_epoch <= start_step:
+                continue  # epoch completed before the checkpoint
             self.model.train()
             epoch_loss = None
             with tqdm(total=len(self.train_dataloader), desc=f"Epoch {epoch + 1}/{num_epochs}",
                       disable=rank != 0) as pbar:
                 for it, batch in enumerate(self.train_dataloader):
+                    if epoch * steps_per_epoch + it < start_step:
+                        pbar.update(1)
+                        continue
                     loss = self.training_step(batch)
                     epoch_loss = loss.clone() if epoch_loss is None else epoch_loss + loss
                     pbar.update(1)
@@ -186,11 +200,15 @@ class CLIPAdapterTrainer:
 
     # ------------------------------------------------------------------ true resume (not in the reference)
     def save_training_state(self, path):
+        """Everything `train()` needs to continue bit-identically: the trainable parameters (the optimiser's arena),
+        both Adam moments, the step counter, the learning rate and the position in the schedule."""
         torch.save({"optimizer": self.optimizer.state_dict(), "global_step": self._global_step,
                     "total_steps": self._total_steps}, path)
 
     def load_training_state(self, path):
         sd = torch.load(path, map_location=next(self.model.parameters()).device)
         self.optimizer.load_state_dict(sd["optimizer"])
+        self.optimizer.broadcast_from(0)  # data parallel: the rank(s) that did not read the file follow rank 0
         self._global_step = sd["global_step"]
         self._total_steps = sd["total_steps"]
+        self._resumed = True
