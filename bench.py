@@ -11,11 +11,11 @@ image/caption pairs per GPU (weak scaling).  Prints ONE JSON line (rank 0).
   e2e       images/s through the public API (DevicePrefetcher + CLIPAdapterTrainer.training_step) from pinned
             HOST buffers, H2D of every batch and a D2H read of every loss inside the timed region
   roofline  the dominant kernel (tcgen05 dense-layer GEMM): algorithmic FLOPs of its launches / their CUDA-event
-            time inside an instrumented step, against the measured bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference path (fp32 PyTorch on the host cores), bounded sample
+            time inside instrumented steps (median of 10), against the measured bf16 peaks of MEASURED_PEAKS.json
+  cpu_baseline  the reference path on the host cores (fp32), bounded sample: the unmodified reference modules staged
+            into oracle/_ref/ (kind "reference"), or the oracle port when they did not travel (kind "port")
 
---impl reference times that CPU path alone (the reference is pure Python and /root/reference does not travel
-to the GPU box, so the arm runs the oracle port: kind "port").
+--impl reference times that CPU path alone.
 """
 from __future__ import annotations
 
@@ -54,6 +54,17 @@ def _peaks():
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_step_rate(steps: int, warmup: int, batch: int = 8):
+    """The reference path on the host cores, fp32: the UNMODIFIED reference modules (model_m.CLIPWithAdapters +
+    trainer.CLIPAdapterTrainer.train, staged into oracle/_ref/ by oracle/stage_reference.py; kind "reference") when they
+    travelled with the snapshot, else the oracle port of the same step (kind "port")."""
+    from oracle import ref_harness as H
+
+    if H.available():
+        return H.reference_step_rate(MODEL, steps, warmup, batch)
+    return cpu_port_step_rate(steps, warmup, batch)
+
+
+def cpu_port_step_rate(steps: int, warmup: int, batch: int = 8):
     """Oracle port of the Track-M train step (model_m.py forward + trainer.py:91-99) on the host cores, fp32."""
     import torch
 
@@ -165,9 +176,9 @@ def run_native_arm(args):
     import torch
     import torch.distributed as dist
 
-    from oracle import clip_oracle as O  # weight-container builder + FLOP accounting + cpu_baseline only
     from vlm_clip_b200 import _native as N
     from vlm_clip_b200 import ops
+    from vlm_clip_b200.configs import flops_per_pair, random_init_clip
     from vlm_clip_b200.data import DevicePrefetcher
     from vlm_clip_b200.model_m import CLIPWithAdapters
     from vlm_clip_b200.trainer import CLIPAdapterTrainer
@@ -183,11 +194,13 @@ def run_native_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     N.load()
 
-    clip = O.build_hf_clip(MODEL, seed=0).to(dev)
+    clip = random_init_clip(MODEL, seed=0).to(dev)
     torch.manual_seed(1)
     model = CLIPWithAdapters(clip=clip, use_shared_adapters=False, adapter_kind=ADAPTER_KIND).to(dev)
     model.train()
-    trainer = CLIPAdapterTrainer(model, train_dataloader=[None], output_dir="/tmp/vlmclip_bench_ckpt")
+    use_graph = not args.no_graph
+    trainer = CLIPAdapterTrainer(model, train_dataloader=[None], output_dir="/tmp/vlmclip_bench_ckpt", cuda_graph=use_graph)
+    graph_note = None
 
     K, W = args.steps, max(3, args.warmup)
     nrot = 3  # rotate three different batches so no step re-reads the previous step's inputs
@@ -218,54 +231,125 @@ def run_native_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- value: inputs resident in HBM ----------------
-    for i in range(W):
-        trainer.training_step(resident[i % nrot])
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    n0 = N.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        loss = trainer.training_step(resident[i % nrot])
-    e1.record()
-    barrier()
-    n1 = N.launch_count()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
-    ms_step = ms_total / K
-    value = world * BATCH * K / (ms_total / 1e3)
-    final_loss = float(loss.item())
+    def launches_now() -> int:
+        # kernels of the library: counted at enqueue time, plus the ones every graph replay re-launches
+        return int(N.launch_count()) + trainer.graph_replays * trainer.graph_launches_per_step
 
-    # ---------------- e2e: public API from pinned host buffers ----------------
     class _HostLoader:
-        def __init__(self, n):
-            self.n = n
+        def __init__(self, batches, n):
+            self.batches, self.n = batches, n
 
         def __len__(self):
             return self.n
 
         def __iter__(self):
             for i in range(self.n):
-                yield host[i % nrot]
+                yield self.batches[i % len(self.batches)]
 
-    loss_host = torch.empty(K + W, dtype=torch.float32).pin_memory()
-    barrier()
-    it = 0
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for batch in DevicePrefetcher(_HostLoader(W + K), dev):
-        if it == W:
-            barrier()
-            e2.record()
-        l = trainer.training_step(batch)
-        loss_host[it:it + 1].copy_(l.reshape(1), non_blocking=True)  # D2H read of every step's loss
-        it += 1
-    e3.record()
-    barrier()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    def timed_resident(k_steps: int, w_steps: int):
+        """(ms total max over ranks, host ms spent enqueueing the k steps, launches, last loss)"""
+        for i in range(w_steps):
+            trainer.training_step(resident[i % nrot])
+        barrier()
+        n0 = launches_now()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h0 = time.perf_counter()
+        loss = None
+        for i in range(k_steps):
+            loss = trainer.training_step(resident[i % nrot])
+        h1 = time.perf_counter()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), (h1 - h0) * 1e3, launches_now() - n0, loss
+
+    def timed_e2e(batches, k_steps: int, w_steps: int):
+        """Public API from pinned HOST buffers: DevicePrefetcher (H2D of every batch) + training_step + D2H of every loss."""
+        loss_host = torch.empty(k_steps + w_steps, dtype=torch.float32).pin_memory()
+        barrier()
+        it = 0
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.perf_counter()
+        for batch in DevicePrefetcher(_HostLoader(batches, w_steps + k_steps), dev):
+            if it == w_steps:
+                barrier()
+                e2.record()
+                h0 = time.perf_counter()
+            l = trainer.training_step(batch)
+            loss_host[it:it + 1].copy_(l.reshape(1), non_blocking=True)  # D2H read of every step's loss
+            it += 1
+        h1 = time.perf_counter()
+        e3.record()
+        barrier()
+        return max_over_ranks(e2.elapsed_time(e3)), (h1 - h0) * 1e3
+
+    # ---------------- settle: bring the board to its sustained, power-capped state before anything is timed -----------
+    # (the driver's default K = 20 is a 0.25 s region; without this it runs at burst clocks while the roofline fraction is
+    # quoted against the SUSTAINED peak)
+    t_settle = time.perf_counter()
+    n_settle = 0
+    try:
+        while time.perf_counter() - t_settle < args.settle_s or n_settle < trainer.graph_warmup_steps + 2:
+            trainer.training_step(resident[n_settle % nrot])
+            n_settle += 1
+            if n_settle % 8 == 0:
+                torch.cuda.synchronize()
+    except Exception as e:  # a capture failure must not cost the round its benchmark line: same kernels, eager launches
+        if not use_graph:
+            raise
+        graph_note = f"capture failed, eager launches used: {type(e).__name__}: {e}"
+        sys.stderr.write(graph_note + "\n")
+        torch.cuda.synchronize()
+        trainer.cuda_graph = False
+        use_graph = False
+
+    # ---------------- value: inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, host_ms, n_launch, loss = timed_resident(K, W)
+    clocks = sampler.stop()
+    ms_step = ms_total / K
+    value = world * BATCH * K / (ms_total / 1e3)
+    final_loss = float(loss.item())
+
+    # ---------------- e2e: public API from pinned host buffers ----------------
+    ms_e2e, host_ms_e2e = timed_e2e(host, K, W)
     e2e_value = world * BATCH * K / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    # one isolated pinned-host -> device copy of a pixel batch: what this box's PCIe path delivers
+    pb = host[0]["pixel_values"]
+    dst = torch.empty_like(resident[0]["pixel_values"])
+    dst.copy_(pb, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        dst.copy_(pb, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * pb.numel() * pb.element_size() / (c0.elapsed_time(c1) / 1e3) / 1e9
+    del dst
+
+    # ---------------- e2e from uint8 frames (a quarter of the H2D bytes; fused preprocessing on the GPU) -------------
+    host_u8 = []
+    for b in host:
+        fr = torch.randint(0, 256, (BATCH, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
+        host_u8.append({"input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "pixel_values": fr})
+    Ku = max(5, K // 2)
+    ms_u8, _ = timed_e2e(host_u8, Ku, trainer.graph_warmup_steps + 3)
+    h2d_u8 = sum(v.numel() * v.element_size() for v in host_u8[0].values())
+
+    # ---------------- the same step with eager launches (no CUDA graph), for comparison ----------------
+    eager = None
+    if use_graph:
+        trainer.cuda_graph = False
+        Ke = max(5, K // 2)
+        ms_eager, host_eager, _, _ = timed_resident(Ke, 3)
+        ms_eager_e2e, host_eager_e2e = timed_e2e(host, Ke, 3)
+        trainer.cuda_graph = True
+        eager = {"what": "same step, kernels enqueued one by one (two native tower calls + ~60 interpreter-level ops per step)",
+                 "ms_per_step": ms_eager / Ke, "host_enqueue_ms_per_step": host_eager / Ke,
+                 "e2e_ms_per_step": ms_eager_e2e / Ke, "e2e_host_enqueue_ms_per_step": host_eager_e2e / Ke, "steps": Ke}
 
     # ---------------- opt-in shortcut variant (reported beside the headline, never as it) ----------------
     # Track M pools the causal text tower at token 0 (the reference's BOS quirk, SURVEY.md 8a-6), so the text tower on
@@ -275,36 +359,42 @@ def run_native_arm(args):
     # (SURVEY.md 8d).
     model.text_token0_only = True
     model.vision_cls_only_last_layer = True
-    Ks = max(3, K // 4)
-    for i in range(3):
-        trainer.training_step(resident[i % nrot])
-    barrier()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e4.record()
-    for i in range(Ks):
-        loss_s = trainer.training_step(resident[i % nrot])
-    e5.record()
-    barrier()
-    ms_short = max_over_ranks(e4.elapsed_time(e5)) / Ks
+    Ks = max(5, K // 4)
+    ms_short_total, _, _, _ = timed_resident(Ks, trainer.graph_warmup_steps + 3)
+    ms_short = ms_short_total / Ks
     model.text_token0_only = False
     model.vision_cls_only_last_layer = False
 
-    # ---------------- roofline of the dominant kernel (instrumented step) ----------------
-    # (towers serialised on one stream for this step only, so that a launch's event pair brackets that kernel alone)
+    # ---------------- roofline of the dominant kernel (instrumented, eager steps) ----------------
+    # (towers serialised on one stream, so that a launch's event pair brackets that kernel alone; every instrumented
+    # step is a whole train step, its GEMM launches are timed one by one)
     overlap = model.overlap_towers
     model.overlap_towers = False
-    ops.PROFILE = {"gemm": []}
-    trainer.training_step(resident[0])
-    torch.cuda.synchronize()
+    trainer.cuda_graph = False
+    sampler2 = ClockSampler(local)
+    sampler2.start()
+    per_step = []
+    n_gemm = 0
+    for r in range(max(1, args.roofline_steps)):
+        ops.PROFILE = {"gemm": []}
+        trainer.training_step(resident[r % nrot])
+        torch.cuda.synchronize()
+        rec = ops.PROFILE["gemm"]
+        ops.PROFILE = None
+        g_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+        g_fl = sum(f for _, _, f in rec)
+        n_gemm = len(rec)
+        per_step.append((g_fl / (g_ms / 1e3) / 1e12, g_ms))
+    clocks_roof = sampler2.stop()
     model.overlap_towers = overlap
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.PROFILE["gemm"])
-    gemm_fl = sum(f for _, _, f in ops.PROFILE["gemm"])
-    n_gemm = len(ops.PROFILE["gemm"])
-    ops.PROFILE = None
+    trainer.cuda_graph = use_graph
     peaks, peak_kind = _peaks()
-    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    fl = O.flops_per_pair(MODEL)
+    peak_sus = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    peak_burst = float(peaks["bf16_tflops"])
+    ach = sorted(a for a, _ in per_step)
+    achieved = statistics.median(ach)
+    gemm_ms = statistics.median(m for _, m in per_step)
+    fl = flops_per_pair(MODEL)
     step_tf = fl["pair"] * BATCH / 1e12
     traffic = None
     tf = ROOT / "profiles" / "gemm_traffic.json"
@@ -320,18 +410,32 @@ def run_native_arm(args):
             "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
             "init": "random (seed 0), no checkpoints offline",
             "l2": f"3 rotating input batches; {BATCH * 3 * 224 * 224 * 4 / 1e6:.0f} MB pixel batch and >1 GB of activations per step exceed the 126 MB L2",
+            "residual_stream": model._backbone().residual,
+            "launch": ("whole step captured in ONE CUDA graph per batch signature and replayed (towers on two branches, heads, "
+                       "loss, backward, NCCL, clip + AdamW); per step the host copies the batch into the graph's input slot "
+                       "(device to device) and launches the graph") if use_graph else
+                      ("eager launches" + (f" ({graph_note})" if graph_note else "")),
+            "settle": f"{n_settle} untimed steps ({time.perf_counter() - t_settle:.1f} s incl. graph capture) before the {W} warm-up "
+                      "steps, so that the timed region runs at the sustained power-capped clock",
             "algorithmic_tflop_per_step_per_gpu": step_tf,
             "step_tflops_per_gpu": step_tf / (ms_step / 1e3),
-            "step_frac_of_bf16_sustained_peak": step_tf / (ms_step / 1e3) / peak_tf,
+            "step_frac_of_bf16_sustained_peak": step_tf / (ms_step / 1e3) / peak_sus,
+            "step_frac_of_bf16_burst_peak": step_tf / (ms_step / 1e3) / peak_burst,
+            "host_enqueue_ms_per_step": host_ms / K,
             "final_loss": final_loss,
-            "streams": ("frozen towers on two private CUDA streams (they start on the input-ready event, so they overlap the "
-                        "previous step's adapter backward / AdamW); adapters, loss, backward, optimizer on the main stream")
+            "streams": ("frozen towers on two private CUDA streams; adapters, loss, backward, optimizer on the main stream")
             if model.overlap_towers else "single stream",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": int(n1 - n0),
+                "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_ms_e2e / K,
+                "h2d_gbs_needed_to_hide_copy": h2d / (ms_e2e / K / 1e3) / 1e9, "h2d_gbs_isolated_copy": h2d_gbs,
+                "uint8_frames_variant": {
+                    "what": "same public API fed decoded uint8 frames [B, 224, 224, 3] (resize / scale / normalise fused into "
+                            "the patch extraction on the GPU) instead of fp32 pixel_values: a quarter of the H2D bytes",
+                    "value": world * BATCH / (ms_u8 / Ku / 1e3), "unit": UNIT, "ms_per_step": ms_u8 / Ku,
+                    "h2d_bytes_per_step": h2d_u8, "steps": Ku}},
+        "gpu_launches": int(n_launch),
         "shortcut_variant": {
             "what": "text tower evaluated on token 0 only (result-identical for Track M's BOS pooling under the causal mask) and "
                     "last vision layer evaluated for the CLS row only after its QKV GEMM; opt-in flags "
@@ -340,14 +444,19 @@ def run_native_arm(args):
             "executed_tflop_per_step_per_gpu": ((fl["image"] - _cls_only_skipped_flops(MODEL)) * BATCH
                                                 + fl["caption"] * BATCH / 77.0) / 1e12,
         },
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
+                     "frac": achieved / peak_sus if peak_sus else None, "traffic": traffic,
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_per_step": n_gemm,
                      "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms_step,
-                     "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a step)"},
+                     "instrumented_steps": len(per_step), "achieved_min": ach[0], "achieved_max": ach[-1],
+                     "frac_of_burst_peak": achieved / peak_burst if peak_burst else None, "peak_burst": peak_burst,
+                     "sm_mhz_median_during_instrumented_steps": clocks_roof.get("sm_mhz"),
+                     "peak_source": f"{peak_kind} bf16_tflops_sustained (kernel timed inside a step); burst = bf16_tflops"},
     }
+    if eager is not None:
+        line["eager_variant"] = eager
     if world == 1 and not args.no_full_finetune:
-        line["full_finetune_variant"] = _full_finetune_leg(dev, fl, peak_tf)
+        line["full_finetune_variant"] = _full_finetune_leg(dev, fl, peak_sus)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_reference_step_rate(steps=3, warmup=1)
         line["cpu_baseline"] = base
@@ -364,13 +473,13 @@ def _full_finetune_leg(dev, fl, peak_tf, steps: int = 5):
     Its own model instance; a failure here is reported in the record and never touches the headline numbers."""
     import torch
 
-    from oracle import clip_oracle as O
     from vlm_clip_b200 import _native as N
+    from vlm_clip_b200.configs import random_init_clip
     from vlm_clip_b200.model_m import CLIPWithAdapters
     from vlm_clip_b200.trainer import CLIPAdapterTrainer
 
     try:
-        clip = O.build_hf_clip(MODEL, seed=0).to(dev)
+        clip = random_init_clip(MODEL, seed=0).to(dev)
         model = CLIPWithAdapters(clip=clip, freeze_clip=False, use_text_adapter=False, use_vision_adapter=False,
                                  use_shared_adapters=False).to(dev)
         model.train()
@@ -406,10 +515,9 @@ def _full_finetune_leg(dev, fl, peak_tf, steps: int = 5):
 
 def _cls_only_skipped_flops(model_name: str) -> float:
     """FLOPs of the last vision layer that the CLS-only evaluation does not execute (per image)."""
-    from oracle import clip_oracle as O
+    from vlm_clip_b200.configs import CLIP_DIMS
 
-    v = O.CLIP_DIMS[model_name].vision
-    S, D, F = v.seq, v.width, v.mlp
+    D, _, _, F, S = CLIP_DIMS[model_name][0]
     return float((S - 1) * (2 * D * D + 4 * D * F) + 4 * (S - 1) * S * D)
 
 
@@ -435,6 +543,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue the step's kernels one by one instead of replaying a CUDA graph")
+    ap.add_argument("--settle-s", type=float, default=1.5, help="seconds of untimed steps before the warm-up (sustained clocks)")
+    ap.add_argument("--roofline-steps", type=int, default=10, help="instrumented steps behind the roofline object")
     ap.add_argument("--no-full-finetune", action="store_true", help="skip the config-5 (full fine-tune) comparison leg")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
                     help="cfg2 (default, the headline): ViT-B/16 + bottleneck adapters, 256 pairs per GPU.  cfg3 (BASELINE "

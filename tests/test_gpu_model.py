@@ -444,6 +444,44 @@ def test_eval_after_optimizer_steps_sees_updated_weights(cuda, clip_b32):
     assert _rel(t_after, t_ref) < 2e-2, (_rel(t_after, t_ref), _rel(t_before, t_ref))  # ... and eval follows it
 
 
+def test_cuda_graph_step_matches_eager_step(cuda, clip_b32, tmp_path):
+    """CLIPAdapterTrainer(cuda_graph=True): the captured-and-replayed step must be the eager step, bit for bit (same
+    kernels, same order, deterministic reductions), including the learning-rate schedule that is pushed to the device
+    outside the graph and a change of batch shape (new signature -> eager warm-up -> second graph)."""
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    def batch(seed, n):
+        pix, ids, mask = O.synthetic_batch(n, seed=seed)
+        ids[:, 0] = (torch.arange(n) * 7 + seed) % 1000
+        return {"input_ids": ids.to(cuda), "attention_mask": mask.to(cuda), "pixel_values": pix.to(cuda)}
+
+    seq = [batch(30 + i, 4) for i in range(7)] + [batch(50 + i, 6) for i in range(5)]
+    res = {}
+    for mode in (False, True):
+        m = _make_model(cuda, clip_b32, seed=9)
+        tr = CLIPAdapterTrainer(m, seq, learning_rate=1e-3, warmup_steps=3, output_dir=str(tmp_path / f"g{int(mode)}"),
+                                cuda_graph=mode, graph_warmup_steps=2)
+        tr._total_steps = len(seq)
+        tr.optimizer.set_lr(0.0)
+        m.train()
+        losses = [tr.training_step(b).clone() for b in seq]
+        torch.cuda.synchronize()
+        res[mode] = (torch.stack(losses), tr.optimizer.flat.clone(), tr.optimizer.exp_avg_sq.clone(), tr)
+    tr_g = res[True][3]
+    assert tr_g.graph_replays == (7 - 2) + (5 - 2) and len(tr_g._graphs) == 2 and tr_g.graph_launches_per_step > 50
+    assert res[False][3].graph_replays == 0
+    assert torch.equal(res[True][0], res[False][0]), (res[True][0] - res[False][0]).abs().max()
+    assert torch.equal(res[True][1], res[False][1]) and torch.equal(res[True][2], res[False][2])
+    assert int(tr_g.optimizer.step_t.item()) == len(seq)
+    # evaluation / no-grad forward after graphed training sees the updated adapters (they live in the arena the graph writes)
+    tr_g.model.eval()
+    with torch.no_grad():
+        out_g = tr_g.model(**seq[0])
+        res[False][3].model.eval()
+        out_e = res[False][3].model(**seq[0])
+    assert torch.equal(out_g["loss"], out_e["loss"])
+
+
 def test_resume_continues_like_an_uninterrupted_run(cuda, clip_b32, tmp_path):
     """SURVEY.md 8f-4 (the reference has no resume, trainer.py:157-167): 6 steps in one go == 3 steps, save, fresh
     trainer + model, load, 3 more steps.  Compares parameters, both Adam moments, the step counter and the position in

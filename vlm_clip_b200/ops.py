@@ -812,11 +812,18 @@ class FusedAdamW:
     def set_lr(self, lr: float):
         self.param_groups[0]["lr"] = float(lr)
 
-    def step(self):
-        lr_host = float(self.param_groups[0]["lr"])  # an LR scheduler writes here (trainer.py:58-62,99)
+    def push_lr(self):
+        """Copy the host-side learning rate (an LR scheduler writes param_groups[0]["lr"], trainer.py:58-62,99) into the
+        device scalar the kernel reads.  Called by step(); a CUDA-graph replay of step() calls it BEFORE the replay, the
+        captured step itself must not contain the fill (it would bake one value into the graph)."""
+        lr_host = float(self.param_groups[0]["lr"])
         if lr_host != self._lr_on_device:
             self.lr.fill_(lr_host)
             self._lr_on_device = lr_host
+
+    def step(self):
+        if not torch.cuda.is_current_stream_capturing():
+            self.push_lr()
         N.check(
             N.load().vlmclip_adamw_clip_step(N.ptr(self.flat), N.ptr(self.grad), N.ptr(self.exp_avg),
                                              N.ptr(self.exp_avg_sq), self.n, N.ptr(self.lr), self.betas[0],
