@@ -411,9 +411,11 @@ def run_native_arm(args):
             "init": "random (seed 0), no checkpoints offline",
             "l2": f"3 rotating input batches; {BATCH * 3 * 224 * 224 * 4 / 1e6:.0f} MB pixel batch and >1 GB of activations per step exceed the 126 MB L2",
             "residual_stream": model._backbone().residual,
-            "launch": ("whole step captured in ONE CUDA graph per batch signature and replayed (towers on two branches, heads, "
-                       "loss, backward, NCCL, clip + AdamW); per step the host copies the batch into the graph's input slot "
-                       "(device to device) and launches the graph") if use_graph else
+            "launch": ("whole step captured as TWO CUDA graphs per batch signature and replayed: G_T (both frozen towers on two "
+                       "branches -> fp32 pooled rows) on its own stream, G_H (final LN, adapters, projections, loss, backward, "
+                       "NCCL, clip + AdamW) on the caller's; G_T of step k+1 runs under G_H of step k (the towers do not depend "
+                       "on the optimizer); per step the host copies the batch into G_T's input slot (device to device) and "
+                       "launches two graphs") if use_graph else
                       ("eager launches" + (f" ({graph_note})" if graph_note else "")),
             "settle": f"{n_settle} untimed steps ({time.perf_counter() - t_settle:.1f} s incl. graph capture) before the {W} warm-up "
                       "steps, so that the timed region runs at the sustained power-capped clock",

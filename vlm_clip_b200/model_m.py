@@ -205,9 +205,12 @@ class CLIPWithAdapters(nn.Module):
         return input_ids, attention_mask
 
     def _text_head(self, bb, hidden, B, S):
-        # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32, read from both terms of
-        # the residual stream
-        tok0 = ops.layernorm_f32(hidden.rows_f32(B, S * bb.Dt, bb.Dt), bb.final_ln_w, bb.final_ln_b, bb.eps_t)
+        return self._text_head_rows(bb, hidden.rows_f32(B, S * bb.Dt, bb.Dt))
+
+    def _text_head_rows(self, bb, rows):
+        """rows: fp32 [B, Dt] = token 0 of every caption's pre-final-LN state (both terms of the residual stream)."""
+        # final_layer_norm on the rows that are consumed (token 0 of every caption), in fp32
+        tok0 = ops.layernorm_f32(rows, bb.final_ln_w, bb.final_ln_b, bb.eps_t)
         if self.use_text_adapter:
             tok0 = self.text_adapter(tok0)
         if self.use_shared_adapters:
@@ -259,9 +262,12 @@ class CLIPWithAdapters(nn.Module):
 
     def _image_head(self, bb, hidden, B, seq=None):
         seq = bb.Sv if seq is None else seq
-        # the CLS rows in fp32 (hi + lo of the residual stream); the adapter is position-wise, so evaluating it on row 0
-        # of every sequence is result-identical to the reference's all-token call followed by [:, 0, :] (model_m.py:116-122)
-        cls = hidden.rows_f32(B, seq * bb.Dv, bb.Dv)
+        return self._image_head_rows(bb, hidden.rows_f32(B, seq * bb.Dv, bb.Dv))
+
+    def _image_head_rows(self, bb, cls):
+        """cls: fp32 [n, Dv] = the CLS rows (hi + lo of the residual stream).  The adapter is position-wise, so evaluating
+        it on row 0 of every sequence is result-identical to the reference's all-token call followed by [:, 0, :]
+        (model_m.py:116-122)."""
         if self.use_vision_adapter:
             cls = self.vision_adapter(cls)
         return ops.linear_f32(cls, bb.visual_projection)
@@ -269,8 +275,9 @@ class CLIPWithAdapters(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, pixel_values=None, return_loss=True, *, inputs_ready=None):
         """Same contract as the reference (model_m.py:127-176): 5-key dict with the loss, 2-key dict without."""
         both = input_ids is not None and attention_mask is not None and pixel_values is not None
-        if both and self.overlap_towers and pixel_values.is_cuda and not self._full_finetune():
-            text_features, image_features = self._both_towers(input_ids, attention_mask, pixel_values, inputs_ready)
+        if both and pixel_values.is_cuda and not self._full_finetune():
+            rows_t, rows_v = self.tower_pooled(input_ids, attention_mask, pixel_values, inputs_ready)
+            text_features, image_features = self.features_from_pooled(rows_t, rows_v)
         else:
             if input_ids is not None and attention_mask is not None:
                 text_features = self.get_text_features(input_ids, attention_mask)
@@ -283,26 +290,61 @@ class CLIPWithAdapters(nn.Module):
                 image_features = None
 
         if return_loss and text_features is not None and image_features is not None:
-            scale = self._logit_scale_exp()
-            ls = self.clip.logit_scale
-            ls_param = ls if (ls.requires_grad and torch.is_grad_enabled()) else None
-            txt_all = img_all = None
-            row0 = 0
-            if self._dp_enabled:
-                from .dist import gather_features, world
-
-                if world(self._dp_group)[0] > 1:
-                    txt_all, img_all, row0 = gather_features(text_features, image_features, self._dp_group)
-            loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0,
-                                                            logit_scale=ls_param)
-            return {
-                "loss": loss,
-                "text_features": t_n,
-                "image_features": i_n,
-                "logits_per_text": logits_per_text,
-                "logits_per_image": logits_per_text.t(),
-            }
+            return self._loss_outputs(text_features, image_features)
         return {"text_features": text_features, "image_features": image_features}
+
+    def _loss_outputs(self, text_features, image_features):
+        """model_m.py:146-171: the 5-key dict with the symmetric InfoNCE loss (global batch under data parallelism)."""
+        scale = self._logit_scale_exp()
+        ls = self.clip.logit_scale
+        ls_param = ls if (ls.requires_grad and torch.is_grad_enabled()) else None
+        txt_all = img_all = None
+        row0 = 0
+        if self._dp_enabled:
+            from .dist import gather_features, world
+
+            if world(self._dp_group)[0] > 1:
+                txt_all, img_all, row0 = gather_features(text_features, image_features, self._dp_group)
+        loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0,
+                                                        logit_scale=ls_param)
+        return {
+            "loss": loss,
+            "text_features": t_n,
+            "image_features": i_n,
+            "logits_per_text": logits_per_text,
+            "logits_per_image": logits_per_text.t(),
+        }
+
+    # ------------------------------------------------------------------ the step in two halves (frozen towers | trainable rest)
+    def tower_pooled(self, input_ids, attention_mask, pixel_values, inputs_ready=None):
+        """Frozen half of forward(): both towers -> the only rows the rest of the model reads, in fp32:
+        (token 0 of every caption BEFORE final_layer_norm [B, Dt], CLS row of every image / frame [n, Dv]).
+        Independent of every trainable parameter, so it may run ahead of the previous step's optimizer update
+        (trainer.CLIPAdapterTrainer captures the two halves as two CUDA graphs and overlaps them across steps)."""
+        bb = self._backbone()
+        if self.overlap_towers:
+            t_hidden, v_hidden, n_img, v_seq = self._both_towers(input_ids, attention_mask, pixel_values, inputs_ready)
+        else:
+            ids, am = self._text_inputs(input_ids, attention_mask)
+            t_hidden = bb.text_stream_pre_ln(ids, am)
+            v_hidden, n_img, v_seq = self._vision_hidden(bb, pixel_values)
+        S = 1 if (self.text_token0_only and input_ids.shape[1] > 1) else input_ids.shape[1]
+        rows_t = t_hidden.rows_f32(input_ids.shape[0], S * bb.Dt, bb.Dt)
+        rows_v = v_hidden.rows_f32(n_img, v_seq * bb.Dv, bb.Dv)
+        return rows_t, rows_v
+
+    def features_from_pooled(self, rows_t, rows_v):
+        """Trainable half of forward() up to the features: final LN, adapters, projections (and the temporal mean-pool
+        when rows_v holds T frames per caption)."""
+        bb = self._backbone()
+        text_features = self._text_head_rows(bb, rows_t)
+        image_features = self._image_head_rows(bb, rows_v)
+        if rows_v.shape[0] != rows_t.shape[0]:  # clips: temporal mean-pool of the per-frame features
+            image_features = ops.mean_pool(image_features, rows_v.shape[0] // rows_t.shape[0])
+        return text_features, image_features
+
+    def loss_from_pooled(self, rows_t, rows_v):
+        return self._loss_outputs(*self.features_from_pooled(rows_t, rows_v))
 
     def _both_towers(self, input_ids, attention_mask, pixel_values, inputs_ready=None):
         """Frozen towers on two private streams, adapters / projections on the caller's stream.
@@ -340,11 +382,7 @@ class CLIPWithAdapters(nn.Module):
         main.wait_stream(vis)
         t_hidden.record_stream(main)
         v_hidden.record_stream(main)
-        text_features = self._text_head(bb, t_hidden, input_ids.shape[0], input_ids.shape[1])
-        image_features = self._image_head(bb, v_hidden, n_img, v_seq)
-        if pixel_values.dim() == 5:  # clips: temporal mean-pool of the per-frame features
-            image_features = ops.mean_pool(image_features, n_img // pixel_values.shape[0])
-        return text_features, image_features
+        return t_hidden, v_hidden, n_img, v_seq
 
     def _logit_scale_exp(self) -> float:
         # logit_scale is a frozen scalar parameter: cache exp() on the host, re-read only when it is modified

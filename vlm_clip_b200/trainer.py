@@ -132,10 +132,10 @@ class CLIPAdapterTrainer:
         """forward -> zero_grad -> backward -> (all-reduce) -> clip + AdamW -> schedule.  Returns the loss tensor.
 
         With `cuda_graph=True` the whole step (both towers on their streams, heads, loss, backward, NCCL, optimiser) is
-        captured once per batch signature and replayed: the host then does O(1) work per step (one device-to-device copy
-        of the batch into the graph's input slot, one graph launch) instead of enqueueing ~230 kernels through the
-        interpreter, which is what made the end-to-end rate depend on the host (14.6 vs 11.7 ms per step on a
-        slow box)."""
+        captured once per batch signature as two CUDA graphs and replayed (`_graphed_step`): the host then does O(1)
+        work per step (one device-to-device copy of the batch into the graph's input slot, two graph launches) instead
+        of enqueueing ~230 kernels through the interpreter, which is what made the end-to-end rate depend on the host
+        (14.6 vs 11.7 ms per step on a slow box)."""
         device = next(self.model.parameters()).device
         batch = {k: v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
         if self.cuda_graph and self._graphable(batch):
@@ -158,40 +158,87 @@ class CLIPAdapterTrainer:
         return not (hasattr(m, "_full_finetune") and m._full_finetune()) and m.training
 
     def _graphed_step(self, batch):
+        """Two graphs per batch signature, software-pipelined across steps:
+
+          G_T  (stream T)     batch slot -> both frozen towers -> fp32 pooled rows (token 0 / CLS of every sequence)
+          G_H  (caller's)     pooled rows -> final LN, adapters, projections, (all-gather,) loss, backward, (all-reduce,)
+                              clip + AdamW
+
+        The towers do not depend on any trainable parameter, so G_T of step k+1 is launched on its own stream as soon as
+        the batch is on the device and runs under the latency-bound G_H of step k (a few hundred microseconds of small
+        kernels and, under data parallelism, two NCCL collectives).  The hand-over is two small buffers: G_T writes
+        `pooled_T`, the caller's stream copies them to `pooled_H` (1.3 MB) once G_T is done, and the next G_T waits for
+        that copy."""
         keys = ("input_ids", "attention_mask", "pixel_values")
         m = self.model
-        # anything that changes which kernels a step launches belongs to the signature of its graph
+        # anything that changes which kernels a step launches belongs to the signature of its graphs
         sig = tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in keys) + (
             getattr(m, "text_token0_only", False), getattr(m, "vision_cls_only_last_layer", False),
             getattr(m, "overlap_towers", True))
         st = self._graphs.get(sig)
         if st is None:
-            st = self._graphs[sig] = {"eager_left": self.graph_warmup_steps, "graph": None}
-        if st["graph"] is None:
+            st = self._graphs[sig] = {"eager_left": self.graph_warmup_steps, "G_T": None}
+        if st["G_T"] is None:
             if st["eager_left"] > 0:  # first steps of a signature run eagerly: lazy initialisation, allocator warm-up
                 st["eager_left"] -= 1
                 return self._step_body(batch, batch.get("inputs_ready"))
             self._capture(st, batch, keys)
-        for k in keys:
-            st["inputs"][k].copy_(batch[k], non_blocking=True)  # device-to-device, on the launching stream
+        main = torch.cuda.current_stream()
+        T = st["stream_T"]
+        ready = batch.get("inputs_ready")
+        if ready is not None:
+            T.wait_event(ready)      # the batch is complete (DevicePrefetcher's copy event): no need to wait for `main`
+        else:
+            T.wait_stream(main)      # correct, but serialises the towers behind the previous step's tail
+        T.wait_event(st["copied"])   # the previous step's pooled rows have been taken over by `main`
+        with torch.cuda.stream(T):
+            for k in keys:
+                st["inputs"][k].copy_(batch[k], non_blocking=True)  # device-to-device into the graph's input slot
+                batch[k].record_stream(T)
+            st["G_T"].replay()
+            st["towers_done"].record(T)
+        main.wait_event(st["towers_done"])
+        for dst, src in zip(st["pooled_H"], st["pooled_T"]):
+            dst.copy_(src, non_blocking=True)
+        st["copied"].record(main)
         self.optimizer.push_lr()
-        st["graph"].replay()
+        st["G_H"].replay()
         self.graph_replays += 1
         return st["loss"].clone()
 
     def _capture(self, st, batch, keys):
         from . import _native as N
 
+        m = self.model
+        dev = batch["pixel_values"].device
+        main = torch.cuda.current_stream()
+        st["stream_T"] = torch.cuda.Stream(device=dev)
+        st["towers_done"], st["copied"] = torch.cuda.Event(), torch.cuda.Event()
         st["inputs"] = {k: batch[k].clone() for k in keys}
         self.optimizer.push_lr()
-        torch.cuda.current_stream().synchronize()
-        g = torch.cuda.CUDAGraph()
+        main.synchronize()
         n0 = N.launch_count()
-        with torch.cuda.graph(g):
-            st["loss"] = self._step_body(st["inputs"], None)
+        g_t = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_t):
+            with torch.no_grad():
+                st["pooled_T"] = m.tower_pooled(st["inputs"]["input_ids"], st["inputs"]["attention_mask"],
+                                                st["inputs"]["pixel_values"], None)
+        n1 = N.launch_count()
+        st["pooled_H"] = tuple(torch.zeros_like(t) for t in st["pooled_T"])
+        g_h = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_h):
+            loss = m.loss_from_pooled(*st["pooled_H"])["loss"]
+            opt = self.optimizer
+            opt.zero_grad()
+            loss.backward()
+            allreduce_sum_(opt.grad)
+            opt.step()
+            st["loss"] = loss.detach()
         self.graph_launches_per_step = int(N.launch_count() - n0)
-        # the capture only recorded the step: its effects (optimizer step, Adam step counter) happen on replay
-        st["graph"] = g
+        self.graph_launches_towers = int(n1 - n0)
+        # capture only records: the effects of a step (optimizer update, Adam step counter) happen on replay
+        st["copied"].record(main)
+        st["G_T"], st["G_H"] = g_t, g_h
 
     def train(self, num_epochs, save_every=1, eval_every=1):
         from tqdm import tqdm
