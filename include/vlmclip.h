@@ -223,6 +223,33 @@ int vlmclip_clip_loss(const float* txt, const float* img, float logit_scale_exp,
                       float* logits_per_text, float* loss, float* d_txt, float* d_img, float* d_logit_scale,
                       float* workspace, int N, int P, int row0, int nloc, void* stream);
 
+/* The same loss on STRIPS of the logit matrix, three launches instead of eight (csrc/clip_loss.cu).  A rank that owns
+ * rows [row0, row0 + nloc) of the global batch computes Zt = its text rows x all images and Zi = its image rows x all
+ * texts, which give the text-side LSE of its rows and the image-side LSE of its columns.  Under data parallelism the
+ * ranks all-gather their [lse_t | lse_i | loss share] blocks (2 nloc + 1 floats) between the two calls; a single process
+ * passes lse_loc straight on.
+ *   state     fp32 scratch carried from _fwd to _bwd (vlmclip_clip_loss_state_size(N, P, nloc) floats)
+ *   counters  vlmclip_clip_loss_counters(nloc) 32-bit words, ZERO before the first call; every call leaves them zero
+ *   _fwd      txt / img [N, P] (all-gathered, un-normalised) -> txt_n / img_n [N, P], lse_loc [2 nloc], loss_share [1]
+ *             (the loss when nloc == N), logits_per_text [N, N] (optional, nloc == N only)
+ *   _bwd      d_txt / d_img [nloc, P]: gradient of the GLOBAL loss w.r.t. the un-normalised local rows.  lse_all: the
+ *             gathered blocks, text-side LSE of global row r at lse_all[(r / rows_per_rank) * lse_stride + r %
+ *             rows_per_rank], the image-side one rows_per_rank further.  The strips in `state` may cover more rows than
+ *             [row0, row0 + nloc): [strip_row0, strip_row0 + strip_rows), the range the _fwd call was made for.
+ *             workspace: vlmclip_clip_loss_bwd_workspace floats.  d_logit_scale (optional): dL/d(log scale), local share. */
+int64_t vlmclip_clip_loss_state_size(int N, int P, int nloc);
+/* y[i] = a[i] * scalar_dev[0] (the upstream gradient of the scalar loss is a device scalar) */
+int vlmclip_scale_f32(const float* a, const float* scalar_dev, float* y, int64_t n, void* stream);
+int64_t vlmclip_clip_loss_counters(int nloc);
+int64_t vlmclip_clip_loss_bwd_workspace(int N, int P, int nloc);
+int vlmclip_clip_loss_fwd(const float* txt, const float* img, float logit_scale_exp, float* txt_n, float* img_n,
+                          float* logits_per_text, float* lse_loc, float* loss_share, float* state, int32_t* counters, int N,
+                          int P, int row0, int nloc, void* stream);
+int vlmclip_clip_loss_bwd(const float* txt_n, const float* img_n, const float* lse_all, int lse_stride, int rows_per_rank,
+                          float logit_scale_exp, float* d_txt, float* d_img, float* d_logit_scale, float* state,
+                          int32_t* counters, float* workspace, int N, int P, int row0, int nloc, int strip_row0,
+                          int strip_rows, void* stream);
+
 /* Class-prompt head (model_t.py:184-187,213-242; model_v.py:340-343): logits[B,C] = scale * f_img f_txt^T,
  * cross-entropy against int64 labels (hard) or fp32 [B,C] probabilities (soft), mean reduction, plus
  * gradients w.r.t. f_img, f_txt.  probs (optional) = softmax(logits).  group > 1: logits are first

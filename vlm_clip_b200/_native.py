@@ -50,6 +50,12 @@ PROTOTYPES = {
     "vlmclip_linear_f32_dgrad": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vlmclip_clip_loss_workspace": (_i64, [_i, _i]),
     "vlmclip_clip_loss": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vlmclip_clip_loss_state_size": (_i64, [_i, _i, _i]),
+    "vlmclip_clip_loss_counters": (_i64, [_i]),
+    "vlmclip_scale_f32": (_i, [_p, _p, _p, _i64, _p]),
+    "vlmclip_clip_loss_bwd_workspace": (_i64, [_i, _i, _i]),
+    "vlmclip_clip_loss_fwd": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "vlmclip_clip_loss_bwd": (_i, [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vlmclip_class_head": (_i, [_p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vlmclip_class_head_bwd": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _p]),
     "vlmclip_l2norm_rows": (_i, [_p, _p, _p, _p, _i, _i, _p]),

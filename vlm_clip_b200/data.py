@@ -10,28 +10,53 @@ import torch
 
 
 class DevicePrefetcher:
+    """Copies batch k+depth from (pinned) host memory on a side stream while step k computes.
+
+    The device side is a RING of `depth + 1` preallocated slots per batch signature, so the steady state performs no
+    allocation at all: a `cudaMalloc` in the loop synchronises the device, and blocks handed to other streams
+    (`record_stream`) come back to the caching allocator late, which made the first dozens of steps of a run host-bound.
+    A slot is overwritten only after the consumer's stream has passed the point where it asked for the NEXT batch, i.e.
+    after everything it enqueued for the batch that lived in the slot."""
+
     def __init__(self, loader, device, depth: int = 2):
         self.loader = loader
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
+        self._rings = {}
 
     def __len__(self):
         return len(self.loader)
 
+    def _slot(self, batch):
+        sig = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()) if isinstance(v, torch.Tensor))
+        ring = self._rings.get(sig)
+        if ring is None:
+            ring = self._rings[sig] = {"next": 0, "slots": [
+                {"tensors": {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in batch.items()
+                             if isinstance(v, torch.Tensor)}, "free": None} for _ in range(self.depth + 1)]}
+        slot = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+        return slot
+
     def _stage(self, batch):
+        slot = self._slot(batch)
         out = {}
         with torch.cuda.stream(self.stream):
+            if slot["free"] is not None:
+                self.stream.wait_event(slot["free"])  # the step that read this slot last has been enqueued AND finished
             for k, v in batch.items():
                 if isinstance(v, torch.Tensor):
                     if not v.is_cuda and not v.is_pinned():
                         v = v.pin_memory()
-                    out[k] = v.to(self.device, non_blocking=True)
+                    dst = slot["tensors"][k]
+                    dst.copy_(v, non_blocking=True)
+                    out[k] = dst
                 else:
                     out[k] = v
         ev = torch.cuda.Event()
         ev.record(self.stream)
-        return out, ev
+        return out, ev, slot
 
     def __iter__(self):
         it = iter(self.loader)
@@ -42,17 +67,19 @@ class DevicePrefetcher:
         except StopIteration:
             pass
         while queue:
-            batch, ev = queue.pop(0)
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for v in batch.values():
-                if isinstance(v, torch.Tensor):
-                    v.record_stream(torch.cuda.current_stream(self.device))
+            batch, ev, slot = queue.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
             try:
                 queue.append(self._stage(next(it)))
             except StopIteration:
                 pass
             batch["inputs_ready"] = ev  # lets the frozen towers start without waiting for the consumer's stream
             yield batch
+            # the consumer is back for the next batch: whatever it enqueued for this one precedes this event
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            slot["free"] = done
 
 
 class SyntheticPairs(torch.utils.data.Dataset):

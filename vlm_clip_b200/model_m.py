@@ -107,6 +107,7 @@ class CLIPWithAdapters(nn.Module):
         self._ft_towers = None
         self._dp_group = None
         self._dp_enabled = False
+        self.dp_return_logits = False  # data parallel: also return the full N x N logits_per_text (see _loss_outputs)
         # run the two towers on two CUDA streams (VLMCLIP_OVERLAP_TOWERS=0 serialises them, e.g. for per-kernel timing)
         self.overlap_towers = os.environ.get("VLMCLIP_OVERLAP_TOWERS", "1") != "0"
         self._tower_streams = None
@@ -298,15 +299,20 @@ class CLIPWithAdapters(nn.Module):
         scale = self._logit_scale_exp()
         ls = self.clip.logit_scale
         ls_param = ls if (ls.requires_grad and torch.is_grad_enabled()) else None
-        txt_all = img_all = None
+        txt_all = img_all = exchange = None
         row0 = 0
         if self._dp_enabled:
             from .dist import gather_features, world
 
             if world(self._dp_group)[0] > 1:
                 txt_all, img_all, row0 = gather_features(text_features, image_features, self._dp_group)
+                exchange = self._dp_group if self._dp_group is not None else True
         loss, t_n, i_n, logits_per_text = ops.clip_loss(text_features, image_features, scale, txt_all, img_all, row0,
-                                                        logit_scale=ls_param)
+                                                        logit_scale=ls_param, exchange=exchange)
+        if exchange is not None and self.dp_return_logits:
+            # under data parallelism a rank only forms its strips of the global logit matrix; the full [N, N] matrix the
+            # reference's dict carries is computed on request (evaluation scripts), not on the training path
+            logits_per_text = ops.scaled_similarity(t_n, i_n, scale)
         return {
             "loss": loss,
             "text_features": t_n,

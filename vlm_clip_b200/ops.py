@@ -645,57 +645,126 @@ def scaled_similarity(f_img, f_txt, scale: float):
 
 
 # --------------------------------------------------------------------------------------------- heads
+_LOSS_COUNTERS = {}
+
+
+def _loss_counters(dev, n_words: int):
+    """Zeroed int32 words the strip kernels use for their last-arriver reductions (every launch leaves them zero), one
+    buffer per (device, stream): launches on one stream are ordered, launches on different streams must not share it."""
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    buf = _LOSS_COUNTERS.get(key)
+    if buf is None or buf.numel() < n_words:
+        buf = _LOSS_COUNTERS[key] = torch.zeros(max(1024, n_words), device=dev, dtype=torch.int32)
+    return buf
+
+
 class _ClipLossFn(torch.autograd.Function):
-    """Symmetric InfoNCE over the (global) batch; gradients for rows [row0, row0 + nloc) only."""
+    """Symmetric InfoNCE over the (global) batch on strips of the logit matrix (csrc/clip_loss.cu); gradients for rows
+    [row0, row0 + nloc) only.
+
+    exchange=None, nloc == N   single process: 3 launches.
+    exchange=None, nloc <  N   one process stands in for a rank and has no peer to ask: the strips of ALL rows are
+                               computed (every LSE is then local) and only the local rows are differentiated.
+    exchange=group             data parallel: strips of the local rows only; the ranks all-gather their
+                               [lse_t | lse_i | loss share] blocks (2 nloc + 1 floats) between the two kernels.
+    """
 
     @staticmethod
-    def forward(ctx, txt_local, img_local, txt_all, img_all, scale_exp, row0, want_logits, logit_scale=None):
+    def forward(ctx, txt_local, img_local, txt_all, img_all, scale_exp, row0, want_logits, logit_scale=None, exchange=None):
         Ng, P = txt_all.shape
         nloc = txt_local.shape[0]
         dev = txt_all.device
         lib = N.load()
+        srow0, srows = (row0, nloc) if (exchange is not None or nloc == Ng) else (0, Ng)
         txt_n = torch.empty_like(txt_all)
         img_n = torch.empty_like(img_all)
-        logits = torch.empty((Ng, Ng), device=dev, dtype=f32) if want_logits else None
-        loss = torch.empty((1,), device=dev, dtype=f32)
-        d_txt = torch.empty((nloc, P), device=dev, dtype=f32)
-        d_img = torch.empty((nloc, P), device=dev, dtype=f32)
-        ws = torch.empty(lib.vlmclip_clip_loss_workspace(Ng, P), device=dev, dtype=f32)
-        # trainable logit_scale (full fine-tune): the kernel also returns dL/d(log scale) for this rank's rows
-        d_ls = torch.empty((1,), device=dev, dtype=f32) if logit_scale is not None else None
+        logits = torch.empty((Ng, Ng), device=dev, dtype=f32) if (want_logits and srows == Ng) else None
+        block = torch.empty((2 * srows + 1,), device=dev, dtype=f32)  # [lse_t | lse_i | loss share]
+        state = torch.empty(lib.vlmclip_clip_loss_state_size(Ng, P, srows), device=dev, dtype=f32)
+        counters = _loss_counters(dev, lib.vlmclip_clip_loss_counters(srows))
         N.check(
-            lib.vlmclip_clip_loss(N.ptr(txt_all), N.ptr(img_all), float(scale_exp), N.ptr(txt_n), N.ptr(img_n),
-                                  N.ptr(logits), N.ptr(loss), N.ptr(d_txt), N.ptr(d_img), N.ptr(d_ls), N.ptr(ws), Ng, P,
-                                  int(row0), nloc, N.stream()), "vlmclip_clip_loss")
-        ctx.save_for_backward(d_txt, d_img)
+            lib.vlmclip_clip_loss_fwd(N.ptr(txt_all), N.ptr(img_all), float(scale_exp), N.ptr(txt_n), N.ptr(img_n),
+                                      N.ptr(logits), N.ptr(block), C_ptr_off(block, 2 * srows), N.ptr(state),
+                                      N.ptr(counters), Ng, P, int(srow0), int(srows), N.stream()), "vlmclip_clip_loss_fwd")
+        if exchange is not None:
+            import torch.distributed as dist
+
+            ws = dist.get_world_size(exchange if exchange is not True else None)
+            gathered = torch.empty((ws, 2 * nloc + 1), device=dev, dtype=f32)
+            dist.all_gather_into_tensor(gathered, block.view(1, -1), group=None if exchange is True else exchange)
+            loss = gathered[:, 2 * nloc].sum()  # the one reduction left to torch: `ws` floats
+            lse_all, lse_stride, rows_per_rank = gathered, 2 * nloc + 1, nloc
+        else:
+            loss = block[2 * srows]
+            lse_all, lse_stride, rows_per_rank = block, 2 * srows + 1, srows
+        # (autograd.Function.forward runs under no_grad: whether a gradient is wanted is read off the inputs)
+        need_grad = txt_local.requires_grad or img_local.requires_grad or (logit_scale is not None)
+        d_txt = d_img = d_ls = None
+        if need_grad:
+            d_txt = torch.empty((nloc, P), device=dev, dtype=f32)
+            d_img = torch.empty((nloc, P), device=dev, dtype=f32)
+            # trainable logit_scale (full fine-tune): also dL/d(log scale) for this rank's rows
+            d_ls = torch.empty((1,), device=dev, dtype=f32) if logit_scale is not None else None
+            ws_b = torch.empty(lib.vlmclip_clip_loss_bwd_workspace(Ng, P, nloc), device=dev, dtype=f32)
+            N.check(
+                lib.vlmclip_clip_loss_bwd(N.ptr(txt_n), N.ptr(img_n), N.ptr(lse_all), int(lse_stride), int(rows_per_rank),
+                                          float(scale_exp), N.ptr(d_txt), N.ptr(d_img), N.ptr(d_ls), N.ptr(state),
+                                          N.ptr(counters), N.ptr(ws_b), Ng, P, int(row0), nloc, int(srow0), int(srows),
+                                          N.stream()), "vlmclip_clip_loss_bwd")
+            ctx.save_for_backward(d_txt, d_img)
+        ctx.has_grad = need_grad
         ctx.d_ls = d_ls
         ctx.ls_shape = tuple(logit_scale.shape) if logit_scale is not None else None
         ctx.mark_non_differentiable(txt_n, img_n)
         if logits is not None:
             ctx.mark_non_differentiable(logits)
-            return loss[0], txt_n, img_n, logits
-        return loss[0], txt_n, img_n, torch.empty(0, device=dev)
+            return loss, txt_n, img_n, logits
+        return loss, txt_n, img_n, torch.empty(0, device=dev)
 
     @staticmethod
     def backward(ctx, dloss, *_):
+        if not ctx.has_grad:
+            return (None,) * 9
         d_txt, d_img = ctx.saved_tensors
-        d_ls = (ctx.d_ls * dloss).reshape(ctx.ls_shape) if ctx.d_ls is not None else None
-        return d_txt * dloss, d_img * dloss, None, None, None, None, None, d_ls
+        d_ls = None
+        if ctx.d_ls is not None:
+            d_ls = _scale_by(ctx.d_ls, dloss).reshape(ctx.ls_shape)
+        return _scale_by(d_txt, dloss), _scale_by(d_img, dloss), None, None, None, None, None, d_ls, None
+
+
+def _scale_by(g, dloss):
+    """g * dloss with dloss a 0-d tensor (the upstream gradient of the scalar loss): on the library's kernel, not an
+    aten elementwise op (vlmclip_scale_f32 broadcasts a device scalar)."""
+    out = torch.empty_like(g)
+    N.check(N.load().vlmclip_scale_f32(N.ptr(g), N.ptr(dloss.reshape(1).contiguous()), N.ptr(out), g.numel(), N.stream()),
+            "vlmclip_scale_f32")
+    return out
+
+
+def C_ptr_off(t, off: int):
+    """device pointer of element `off` of a contiguous tensor"""
+    import ctypes
+
+    return ctypes.c_void_p(t.data_ptr() + off * t.element_size())
 
 
 def clip_loss(txt_local, img_local, logit_scale_exp: float, txt_all=None, img_all=None, row0: int = 0,
-              want_logits: bool = True, logit_scale=None):
+              want_logits: bool = True, logit_scale=None, exchange=None):
     """Returns (loss, txt_normalised_all, img_normalised_all, logits_per_text_all).
 
     txt_all / img_all: the all-gathered un-normalised features under data parallelism (default: the local ones).
     logit_scale: the (log) scale PARAMETER when it is trainable (full fine-tune); it then receives its gradient.
+    exchange: a process group (or True for the default group) whose ranks each own `txt_local.shape[0]` consecutive rows:
+    the log-sum-exps are then exchanged instead of being recomputed by every rank (see _ClipLossFn).  The full logit
+    matrix is returned only when this process computes all of it (no exchange); otherwise an empty tensor.
     """
     if txt_all is None:
         txt_all, img_all, row0 = txt_local.detach(), img_local.detach(), 0
     for t in (txt_local, img_local, txt_all, img_all):
         _req(t.dtype == f32 and t.dim() == 2 and t.is_contiguous(), "clip_loss: features must be contiguous fp32 [N, P]")
+    _req(txt_all.shape[1] % 4 == 0, "clip_loss: the projection dim must be a multiple of 4")
     return _ClipLossFn.apply(txt_local, img_local, txt_all, img_all, float(logit_scale_exp), int(row0), want_logits,
-                             logit_scale)
+                             logit_scale, exchange)
 
 
 class _ClassHeadFn(torch.autograd.Function):
@@ -725,7 +794,7 @@ class _ClassHeadFn(torch.autograd.Function):
         if not ctx.have_lab:
             raise N.NativeError("class_head: backward needs labels")
         d_img, d_txt = ctx.saved_tensors
-        return d_img * dloss, d_txt * dloss, None, None, None
+        return _scale_by(d_img, dloss), _scale_by(d_txt, dloss), None, None, None
 
 
 def class_head_loss(f_img, f_txt, scale: float, labels=None, soft_labels=None):
