@@ -73,9 +73,14 @@ def _encoder_fwd(x, lp: List[torch.Tensor], n_layers: int, B: int, S: int, H: in
     return x, saved
 
 
-def _encoder_bwd(dx32, saved, lp, B: int, S: int, H: int, eps: float, causal: bool, key_mask):
+def _encoder_bwd(dx32, saved, lp, B: int, S: int, H: int, eps: float, causal: bool, key_mask, sink=None):
     """Reverse pass over the layers.  dx32: fp32 gradient of the encoder output [M, D].  Returns (dx32 of the encoder
-    input, list of parameter gradients in `lp` order)."""
+    input, list of parameter gradients in `lp` order).
+
+    sink(params, grads) (optional): called as soon as a layer's 16 parameter gradients exist, with the layer's
+    parameters; it takes the gradients over (writes them into `.grad` and may start their all-reduce while the reverse
+    pass continues with the layers below) and this function then reports None for them, so autograd does not
+    accumulate them a second time."""
     D = dx32.shape[1]
     grads: List[Optional[torch.Tensor]] = [None] * len(lp)
     dx16 = ops.cast_bf16(dx32)
@@ -104,6 +109,9 @@ def _encoder_bwd(dx32, saved, lp, B: int, S: int, H: int, eps: float, causal: bo
         grads[o + 0], grads[o + 1] = ops.layernorm_bwd(d_xn1, x, g1, eps, dres=dx32, dx_f32=other32, dx_bf16=dx16)
         dx32, other32 = other32, dx32  # dx32 now holds d x (the layer's input)
         saved[l] = None  # release the layer's activations as the reverse pass moves on
+        if sink is not None:
+            sink(lp[o:o + _NLP], grads[o:o + _NLP])
+            grads[o:o + _NLP] = [None] * _NLP
     return dx32, grads
 
 
@@ -140,7 +148,7 @@ class _VisionTowerFn(torch.autograd.Function):
         S, D = tw.Sv, tw.Dv
         dx32 = torch.zeros((B * S, D), device=d_rows.device, dtype=f32)
         dx32.view(B, S, D)[:, 0].copy_(d_rows)  # only the CLS rows carry gradient
-        dx32, lgrads = _encoder_bwd(dx32, ctx.saved, ctx.lp, B, S, tw.Hv, tw.eps_v, False, None)
+        dx32, lgrads = _encoder_bwd(dx32, ctx.saved, ctx.lp, B, S, tw.Hv, tw.eps_v, False, None, tw.layer_grad_sink)
         ctx.saved = None
         de32 = torch.empty_like(dx32)
         de16 = torch.empty((B * S, D), device=dx32.device, dtype=bf16)
@@ -180,7 +188,7 @@ class _TextTowerFn(torch.autograd.Function):
         dx32 = torch.zeros((B * S, D), device=d_rows.device, dtype=f32)
         d_fin_g, d_fin_b = ops.layernorm_bwd(d_rows.contiguous(), x.view(B, S * D)[:, :D], fin_g, tw.eps_t,
                                              dx_f32=dx32.view(B, S * D)[:, :D])
-        dx32, lgrads = _encoder_bwd(dx32, ctx.saved, ctx.lp, B, S, tw.Ht, tw.eps_t, True, key_mask)
+        dx32, lgrads = _encoder_bwd(dx32, ctx.saved, ctx.lp, B, S, tw.Ht, tw.eps_t, True, key_mask, tw.layer_grad_sink)
         ctx.saved = None
         d_tok = torch.zeros(tok_shape, device=dx32.device, dtype=f32)
         ops.embed_scatter_add(dx32, input_ids.reshape(-1), d_tok)
@@ -240,6 +248,8 @@ class TrainableClipTowers:
         if p.device.type != "cuda":
             raise N.NativeError("TrainableClipTowers needs a CUDA model: the towers only run on the sm_100a library")
         self.clip = clip
+        # data parallel full fine-tune: trainer.BucketedGradAllReduce installs itself here (see _encoder_bwd)
+        self.layer_grad_sink = None
         cfg = clip.config
         vc, tc = cfg.vision_config, cfg.text_config
         self.eps_v, self.eps_t = float(vc.layer_norm_eps), float(tc.layer_norm_eps)

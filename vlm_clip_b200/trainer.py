@@ -94,6 +94,8 @@ class CLIPAdapterTrainer:
         self.graph_replays = 0
         self.graph_launches_per_step = 0
         self._optimizer = None
+        self._buckets = None
+        self.last_allreduce_buckets = 0
         self._global_step = 0
         self._total_steps = None
         self._resumed = False
@@ -123,10 +125,30 @@ class CLIPAdapterTrainer:
         loss = outputs["loss"]
         opt = self.optimizer
         opt.zero_grad()
-        loss.backward()
-        allreduce_sum_(opt.grad)  # no-op in a single process
+        buckets = self._grad_buckets()
+        if buckets is not None:
+            # full fine-tune under data parallelism: per-layer buckets are all-reduced while the reverse pass continues
+            loss.backward()
+            self.last_allreduce_buckets = buckets.finish()
+        else:
+            loss.backward()
+            allreduce_sum_(opt.grad)  # no-op in a single process
         opt.step()
         return loss.detach()
+
+    def _grad_buckets(self):
+        """BucketedGradAllReduce wired into the hand-written tower backward, or None (single process / frozen towers,
+        where the whole arena is 2.6 MB and one all-reduce after the backward is the right size)."""
+        m = self.model
+        _, world, _ = _dist_world()
+        if world == 1 or not (hasattr(m, "_full_finetune") and m._full_finetune()):
+            return None
+        if self._buckets is None:
+            from .dist import BucketedGradAllReduce
+
+            self._buckets = BucketedGradAllReduce(self.optimizer, getattr(m, "_dp_group", None))
+        m._finetune_towers().layer_grad_sink = self._buckets.sink
+        return self._buckets
 
     def training_step(self, batch):
         """forward -> zero_grad -> backward -> (all-reduce) -> clip + AdamW -> schedule.  Returns the loss tensor.
