@@ -468,6 +468,111 @@ def run_native_arm(args):
         dist.destroy_process_group()
 
 
+def run_finetune_arm(args):
+    """BASELINE config 5 as its own bench line (not the headline): full fine-tune of ViT-B/16 (adapters disabled, all
+    151 M CLIP parameters trainable), 256 pairs per GPU, data parallel with the gradient arena all-reduced in per-layer
+    buckets that start inside the backward pass (dist.BucketedGradAllReduce)."""
+    import torch
+    import torch.distributed as dist
+
+    from vlm_clip_b200 import _native as N
+    from vlm_clip_b200.configs import flops_per_pair, random_init_clip
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.load()
+    clip = random_init_clip(MODEL, seed=0).to(dev)
+    model = CLIPWithAdapters(clip=clip, freeze_clip=False, use_text_adapter=False, use_vision_adapter=False,
+                             use_shared_adapters=False).to(dev)
+    model.train()
+    g = torch.Generator().manual_seed(7 + rank)
+    batches = []
+    for _ in range(2):
+        ids = torch.randint(3, 49406, (BATCH, 77), generator=g)
+        ids[:, 0], ids[:, -1] = (torch.arange(BATCH) * 37 + rank) % 49000, 49407
+        batches.append({"input_ids": ids.to(dev), "attention_mask": torch.ones(BATCH, 77, dtype=torch.int64, device=dev),
+                        "pixel_values": torch.randn(BATCH, 3, 224, 224, generator=g).to(dev)})
+    tr = CLIPAdapterTrainer(model, batches, learning_rate=1e-7, output_dir="/tmp/vlmclip_bench_ft", trainable="all")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k_steps, w_steps):
+        for i in range(w_steps):
+            tr.training_step(batches[i % 2])
+        barrier()
+        n0 = N.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = None
+        for i in range(k_steps):
+            loss = tr.training_step(batches[i % 2])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, int(N.launch_count() - n0), float(loss.item())
+
+    K, W = args.steps, max(3, args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, n_launch, final_loss = timed(K, W)
+    clocks = sampler.stop()
+    ms_step = ms_total / K
+    # the same step without any gradient collective (replicas drift apart: timing only), to size the collective's share
+    share = None
+    if world > 1:
+        import vlm_clip_b200.trainer as T
+
+        saved_ar, saved_b = T.allreduce_sum_, tr._grad_buckets
+        T.allreduce_sum_ = lambda t, group=None: t
+        tr._grad_buckets = lambda: None
+        model._finetune_towers().layer_grad_sink = None
+        ms_nocoll, _, _ = timed(max(3, K // 2), 2)
+        T.allreduce_sum_, tr._grad_buckets = saved_ar, saved_b
+        ms_nocoll /= max(3, K // 2)
+        share = {"ms_per_step_without_gradient_allreduce": ms_nocoll, "exposed_collective_ms": ms_step - ms_nocoll,
+                 "exposed_share_of_step": (ms_step - ms_nocoll) / ms_step}
+    fl = flops_per_pair(MODEL)
+    peaks, _ = _peaks()
+    peak_sus = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    tflop = 3.0 * fl["pair"] * BATCH / 1e12
+    n_par = sum(p.numel() for p in tr.trainable_params)
+    line = {
+        "metric": "full fine-tune images/sec (ViT-B/16, bf16)", "value": world * BATCH / (ms_step / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE config 5: CLIP ViT-B/16 full fine-tune (adapters disabled, every CLIP parameter "
+                               "trainable), Track-M step with hand-written tower backward, clip + AdamW over one arena",
+                   "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                   "trainable_parameters": n_par, "gradient_bytes_per_step": 4 * n_par,
+                   "allreduce": f"{tr.last_allreduce_buckets} NCCL all-reduce calls per step: one per encoder layer issued from "
+                                "inside the backward (last layers first) + the remaining arena ranges" if world > 1 else "none",
+                   "algorithmic_tflop_per_step_per_gpu": tflop, "step_tflops_per_gpu": tflop / (ms_step / 1e3),
+                   "step_frac_of_bf16_sustained_peak": tflop / (ms_step / 1e3) / peak_sus, "final_loss": final_loss,
+                   "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30},
+        "clocks": clocks, "gpu_launches": n_launch,
+    }
+    if share is not None:
+        line["collective"] = share
+    if rank == 0:
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _full_finetune_leg(dev, fl, peak_tf, steps: int = 5):
     """BASELINE config 5 beside the headline: the same Track-M step with the adapters disabled and EVERY CLIP parameter
     trainable (`freeze_clip=False`): towers forward from the live fp32 weights, hand-written backward through both
@@ -549,10 +654,11 @@ def main():
     ap.add_argument("--settle-s", type=float, default=1.5, help="seconds of untimed steps before the warm-up (sustained clocks)")
     ap.add_argument("--roofline-steps", type=int, default=10, help="instrumented steps behind the roofline object")
     ap.add_argument("--no-full-finetune", action="store_true", help="skip the config-5 (full fine-tune) comparison leg")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
                     help="cfg2 (default, the headline): ViT-B/16 + bottleneck adapters, 256 pairs per GPU.  cfg3 (BASELINE "
                          "configs[2], not a headline line): ViT-L/14 + PE-CLIP adapters, 512 pairs per GPU = global batch 4096 "
-                         "on 8 GPUs, global contrastive loss over the all-gathered embeddings")
+                         "on 8 GPUs, global contrastive loss over the all-gathered embeddings.  cfg5 (BASELINE configs[4], not a headline line): "
+                         "full fine-tune of ViT-B/16, 256 pairs per GPU, bucketed gradient all-reduce overlapped with the backward")
     args = ap.parse_args()
     if args.workload == "cfg3":
         global MODEL, BATCH, METRIC, WORKLOAD, ADAPTER_KIND
@@ -563,6 +669,8 @@ def main():
         args.no_full_finetune = True
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "cfg5":
+        run_finetune_arm(args)
     else:
         run_native_arm(args)
 
