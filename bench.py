@@ -289,11 +289,15 @@ def run_native_arm(args):
     t_settle = time.perf_counter()
     n_settle = 0
     try:
-        while time.perf_counter() - t_settle < args.settle_s or n_settle < trainer.graph_warmup_steps + 2:
-            trainer.training_step(resident[n_settle % nrot])
-            n_settle += 1
-            if n_settle % 8 == 0:
-                torch.cuda.synchronize()
+        while True:
+            for _ in range(8):  # every rank runs the SAME number of steps: each one contains collectives
+                trainer.training_step(resident[n_settle % nrot])
+                n_settle += 1
+            torch.cuda.synchronize()
+            # the slowest rank's clock decides for everybody
+            if max_over_ranks((time.perf_counter() - t_settle) * 1e3) >= args.settle_s * 1e3 and \
+                    n_settle >= trainer.graph_warmup_steps + 2:
+                break
     except Exception as e:  # a capture failure must not cost the round its benchmark line: same kernels, eager launches
         if not use_graph:
             raise
@@ -331,17 +335,24 @@ def run_native_arm(args):
     del dst
 
     # ---------------- e2e from uint8 frames (a quarter of the H2D bytes; fused preprocessing on the GPU) -------------
-    host_u8 = []
-    for b in host:
-        fr = torch.randint(0, 256, (BATCH, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
-        host_u8.append({"input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "pixel_values": fr})
-    Ku = max(5, K // 2)
-    ms_u8, _ = timed_e2e(host_u8, Ku, trainer.graph_warmup_steps + 3)
-    h2d_u8 = sum(v.numel() * v.element_size() for v in host_u8[0].values())
+    u8_variant = None
+    if not args.lean:
+        host_u8 = []
+        for b in host:
+            fr = torch.randint(0, 256, (BATCH, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
+            host_u8.append({"input_ids": b["input_ids"], "attention_mask": b["attention_mask"], "pixel_values": fr})
+        Ku = max(5, K // 2)
+        ms_u8, _ = timed_e2e(host_u8, Ku, trainer.graph_warmup_steps + 3)
+        u8_variant = {
+            "what": "same public API fed decoded uint8 frames [B, 224, 224, 3] (resize / scale / normalise fused into "
+                    "the patch extraction on the GPU) instead of fp32 pixel_values: a quarter of the H2D bytes",
+            "value": world * BATCH / (ms_u8 / Ku / 1e3), "unit": UNIT, "ms_per_step": ms_u8 / Ku,
+            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_u8[0].values()), "steps": Ku}
+        del host_u8
 
     # ---------------- the same step with eager launches (no CUDA graph), for comparison ----------------
     eager = None
-    if use_graph:
+    if use_graph and not args.lean:
         trainer.cuda_graph = False
         Ke = max(5, K // 2)
         ms_eager, host_eager, _, _ = timed_resident(Ke, 3)
@@ -357,13 +368,24 @@ def run_native_arm(args):
     # (model_m.py:122), so the last vision layer only needs that row after its QKV GEMM; `value` above is the DENSE
     # computation, this is the same step with both flags on and the skipped FLOPs taken out of its TFLOP count
     # (SURVEY.md 8d).
-    model.text_token0_only = True
-    model.vision_cls_only_last_layer = True
-    Ks = max(5, K // 4)
-    ms_short_total, _, _, _ = timed_resident(Ks, trainer.graph_warmup_steps + 3)
-    ms_short = ms_short_total / Ks
-    model.text_token0_only = False
-    model.vision_cls_only_last_layer = False
+    shortcut = None
+    if not args.lean:
+        model.text_token0_only = True
+        model.vision_cls_only_last_layer = True
+        Ks = max(5, K // 4)
+        ms_short_total, _, _, _ = timed_resident(Ks, trainer.graph_warmup_steps + 3)
+        ms_short = ms_short_total / Ks
+        model.text_token0_only = False
+        model.vision_cls_only_last_layer = False
+        fl_ = flops_per_pair(MODEL)
+        shortcut = {
+            "what": "text tower evaluated on token 0 only (result-identical for Track M's BOS pooling under the causal mask) and "
+                    "last vision layer evaluated for the CLS row only after its QKV GEMM; opt-in flags "
+                    "model.text_token0_only / model.vision_cls_only_last_layer, OFF for every other number in this line",
+            "value": world * BATCH / (ms_short / 1e3), "unit": UNIT, "ms_per_step": ms_short, "steps": Ks,
+            "executed_tflop_per_step_per_gpu": ((fl_["image"] - _cls_only_skipped_flops(MODEL)) * BATCH
+                                                + fl_["caption"] * BATCH / 77.0) / 1e12,
+        }
 
     # ---------------- roofline of the dominant kernel (instrumented, eager steps) ----------------
     # (towers serialised on one stream, so that a launch's event pair brackets that kernel alone; every instrumented
@@ -375,7 +397,7 @@ def run_native_arm(args):
     sampler2.start()
     per_step = []
     n_gemm = 0
-    for r in range(max(1, args.roofline_steps)):
+    for r in range(max(1, 2 if args.lean else args.roofline_steps)):
         ops.PROFILE = {"gemm": []}
         trainer.training_step(resident[r % nrot])
         torch.cuda.synchronize()
@@ -432,20 +454,9 @@ def run_native_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_ms_e2e / K,
                 "h2d_gbs_needed_to_hide_copy": h2d / (ms_e2e / K / 1e3) / 1e9, "h2d_gbs_isolated_copy": h2d_gbs,
-                "uint8_frames_variant": {
-                    "what": "same public API fed decoded uint8 frames [B, 224, 224, 3] (resize / scale / normalise fused into "
-                            "the patch extraction on the GPU) instead of fp32 pixel_values: a quarter of the H2D bytes",
-                    "value": world * BATCH / (ms_u8 / Ku / 1e3), "unit": UNIT, "ms_per_step": ms_u8 / Ku,
-                    "h2d_bytes_per_step": h2d_u8, "steps": Ku}},
+                "uint8_frames_variant": u8_variant},
         "gpu_launches": int(n_launch),
-        "shortcut_variant": {
-            "what": "text tower evaluated on token 0 only (result-identical for Track M's BOS pooling under the causal mask) and "
-                    "last vision layer evaluated for the CLS row only after its QKV GEMM; opt-in flags "
-                    "model.text_token0_only / model.vision_cls_only_last_layer, OFF for every other number in this line",
-            "value": world * BATCH / (ms_short / 1e3), "unit": UNIT, "ms_per_step": ms_short, "steps": Ks,
-            "executed_tflop_per_step_per_gpu": ((fl["image"] - _cls_only_skipped_flops(MODEL)) * BATCH
-                                                + fl["caption"] * BATCH / 77.0) / 1e12,
-        },
+        "shortcut_variant": shortcut,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
                      "frac": achieved / peak_sus if peak_sus else None, "traffic": traffic,
                      "kernel": "gemm_bf16_tn_kernel (tcgen05)", "launches_per_step": n_gemm,
@@ -464,8 +475,23 @@ def run_native_arm(args):
         line["cpu_baseline"] = base
     if rank == 0:
         _emit(line)
+    _shutdown(world, trainer)
+
+
+def _shutdown(world: int, trainer=None):
+    """Orderly end of a multi-rank run.  The step's collectives live inside CUDA graphs: the graphs go first (NCCL cannot
+    tear a communicator down under them - `destroy_process_group()` hung for the full 900 s limit of the first 2-GPU
+    run), then a barrier, then the process leaves without running NCCL's destructors."""
+    import torch
+    import torch.distributed as dist
+
+    if trainer is not None:
+        trainer.release_graphs()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_finetune_arm(args):
@@ -569,8 +595,7 @@ def run_finetune_arm(args):
         line["collective"] = share
     if rank == 0:
         _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(world)
 
 
 def _full_finetune_leg(dev, fl, peak_tf, steps: int = 5):
@@ -650,6 +675,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="skip the side legs (eager / uint8 / shortcut variants, 2 roofline steps)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--settle-s", type=float, default=1.5, help="seconds of untimed steps before the warm-up (sustained clocks)")
     ap.add_argument("--roofline-steps", type=int, default=10, help="instrumented steps behind the roofline object")

@@ -295,6 +295,8 @@ int vlmclip_transpose_to_bf16(const void* src, int src_f32, int64_t lds, void* d
                               int group_dst, int group_src, int group_off, void* stream);
 /* fp32 -> bf16 (per-step cast of the trainable master weights, and of the fp32 gradient stream for the next GEMM) */
 int vlmclip_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* acc[i] += float(b[i]), b bf16: a bf16 gradient branch joins the fp32 gradient of a skip connection */
+int vlmclip_add_bf16_into_f32(float* acc, const void* b, int64_t n, void* stream);
 /* out[r] = sum_c x[r, c], x bf16 [R, C] (ldx): bias gradient = row sums of the transposed output gradient */
 int vlmclip_rowsum_bf16(const void* x, int64_t ldx, float* out, int R, int C, void* stream);
 /* out[c] = sum_r x[r*ldx + c], fp32: position / class embedding gradients (sum over the batch), HF:214-217,255-256 */

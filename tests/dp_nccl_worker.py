@@ -50,8 +50,10 @@ def main():
         return m, tr
 
     results = {}
+    trainers = []
     for mode, (dp, graph) in {"single": (False, False), "dp_eager": (True, False), "dp_graph": (True, True)}.items():
         m, tr = make(1 if not dp else 1 + 100 * rank, dp, graph)
+        trainers.append(tr)
         if not dp:
             import vlm_clip_b200.trainer as T
 
@@ -85,10 +87,14 @@ def main():
         if rank == 0:
             print(f"{mode}: loss diff {dl:.2e}, grad rel diff {dg:.2e}, param diff {dp_:.2e}")
     assert torch.equal(results["dp_eager"][0], results["dp_graph"][0])  # replay == eager, bit for bit
+    for tr in trainers:
+        tr.release_graphs()  # NCCL cannot tear a communicator down while graphs holding its kernels exist
     dist.barrier()
+    torch.cuda.synchronize()
     if rank == 0:
-        print("DP_OK")
-    dist.destroy_process_group()
+        print("DP_OK", flush=True)
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -306,6 +306,92 @@ def test_config3_vit_l14_dims_with_peclip_adapters(cuda):
     assert all("adapter" in n for n, p_ in model.named_parameters() if p_.requires_grad)
 
 
+@pytest.mark.parametrize("cls,B,S,D,H", [("ContextAdapter", 3, 257, 1024, 16), ("SharedAdapter", 2, 50, 768, 12),
+                                         ("ContextAdapter", 5, 197, 768, 12)])
+def test_peclip_attention_adapters_forward_backward(cuda, cls, B, S, D, H):
+    """Row 8a-8b: ContextAdapter / SharedAdapter (adapter/peclip.py:21-48) = LayerNorm(MHSA(x, x, x) + x), forward and the
+    hand-written backward (all six parameter tensors and the input) against autograd over the fp32 oracle.  The module
+    computes on the bf16 tensor cores like the towers, so the bounds are bf16 ones (measured 3-6e-3 forward, 1-2e-2 on the
+    gradients; same kernels and bounds as the full-fine-tune backward, tests/test_gpu_backward.py)."""
+    from vlm_clip_b200.adapter import peclip
+
+    torch.manual_seed(17)
+    mod = getattr(peclip, cls)(D, H).to(cuda).train()
+    with torch.no_grad():  # nn.MultiheadAttention / LayerNorm start with zero biases and unit gains: make them matter
+        for p_ in (mod.mhsa.in_proj_bias, mod.mhsa.out_proj.bias, mod.layer_norm.bias):
+            p_.normal_(0, 0.1)
+        mod.layer_norm.weight.uniform_(0.5, 1.5)
+    g = torch.Generator().manual_seed(18)
+    x = (torch.randn(B, S, D, generator=g) * 0.7).to(cuda).requires_grad_(True)
+    w = torch.randn(B, S, D, generator=g).to(cuda)
+    y = mod(x)
+    (y * w).sum().backward()
+    a = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    xr = x.detach().clone().requires_grad_(True)
+    ref = O.mhsa_adapter(xr, a, H)
+    (ref * w).sum().backward()
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert _rel(y, ref) < 1e-2, _rel(y, ref)
+    assert _rel(x.grad, xr.grad) < 3e-2, _rel(x.grad, xr.grad)
+    for k, p_ in mod.named_parameters():
+        gr = a[k].grad
+        assert p_.grad is not None and p_.grad.shape == gr.shape, k
+        cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), gr.flatten(), dim=0).item()
+        assert cos > 0.995 and _rel(p_.grad, gr) < 5e-2, (k, cos, _rel(p_.grad, gr))
+    # only token 0 consumed (how Track M uses the adapter slot): gradient flows from that row alone
+    mod.zero_grad(set_to_none=True)
+    y0 = mod(x.detach())[:, 0, :]
+    (y0 * w[:, 0]).sum().backward()
+    for v in a.values():
+        v.grad = None
+    (O.mhsa_adapter(x.detach(), a, H)[:, 0, :] * w[:, 0]).sum().backward()
+    for k, p_ in mod.named_parameters():
+        cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), a[k].grad.flatten(), dim=0).item()
+        assert cos > 0.99, (k, cos)
+
+
+def test_track_m_with_context_adapter_in_the_vision_slot(cuda):
+    """adapter_kind="peclip_context" (the option BASELINE config 3's "PE-CLIP adapter" can use): TextualAdapter on the
+    text side, ContextAdapter over all 257 patch tokens on the vision side, trained through the loss; eager and the
+    two-graph replay agree bit for bit."""
+    from vlm_clip_b200.model_m import CLIPWithAdapters
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer
+
+    L14 = "openai/clip-vit-large-patch14"
+    clip = O.build_hf_clip(L14, seed=0, vision_layers=2, text_layers=2).to(cuda)
+    for p_ in clip.parameters():
+        p_.requires_grad_(False)
+    sd = {k: v.detach() for k, v in clip.state_dict().items()}
+    torch.manual_seed(3)
+    model = CLIPWithAdapters(clip=clip, use_shared_adapters=False, adapter_kind="peclip_context").to(cuda).train()
+    Bn = 4
+    pix, ids, mask = O.synthetic_batch(Bn, seed=6)
+    ids[:, 0] = torch.arange(Bn) * 101 + 7
+    pix, ids, mask = pix.to(cuda), ids.to(cuda), mask.to(cuda)
+    out = model(input_ids=ids, attention_mask=mask, pixel_values=pix)
+    out["loss"].backward()
+    ta = {k: v.detach().clone().requires_grad_(True) for k, v in model.text_adapter.state_dict().items()}
+    va = {k: v.detach().clone().requires_grad_(True) for k, v in model.vision_adapter.state_dict().items()}
+    t_feat = O.peclip_textual_adapter(O.text_tower(sd, ids, mask, 12), ta)[:, 0] @ sd["text_projection.weight"].t()
+    i_feat = O.mhsa_adapter(O.vision_tower(sd, pix, 16), va, 16)[:, 0] @ sd["visual_projection.weight"].t()
+    ref = O.contrastive_loss(t_feat, i_feat, sd["logit_scale"])
+    ref["loss"].backward()
+    assert _rel(out["image_features"], ref["image_features"]) < FEAT_TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) < 2 * LOSS_TOL
+    for k, p_ in model.vision_adapter.named_parameters():
+        cos = torch.nn.functional.cosine_similarity(p_.grad.flatten(), va[k].grad.flatten(), dim=0).item()
+        assert cos > 0.97, (k, cos)
+    assert all(p_.grad is None for p_ in clip.parameters())
+    batch = {"input_ids": ids, "attention_mask": mask, "pixel_values": pix}
+    losses = {}
+    for graph in (False, True):
+        torch.manual_seed(3)
+        m = CLIPWithAdapters(clip=clip, use_shared_adapters=False, adapter_kind="peclip_context").to(cuda).train()
+        tr = CLIPAdapterTrainer(m, [None], learning_rate=1e-3, output_dir="/tmp/vlmclip_ctx", cuda_graph=graph, graph_warmup_steps=2)
+        losses[graph] = torch.stack([tr.training_step(batch).clone() for _ in range(5)])
+    assert torch.equal(losses[True], losses[False]) and losses[False][-1] < losses[False][0]
+
+
 def test_shared_mhs_adapter_inference(cuda, clip_b32):
     """Row 8a-8: the cross-modal adapter's inference path on the GPU against the fp32 oracle, stand-alone and inside
     CLIPWithAdapters (token-0 evaluation, model_m.py:93-102)."""

@@ -191,22 +191,3 @@ def test_full_finetune_host_logic(tmp_path):
         m(input_ids=ids, attention_mask=mask, pixel_values=pix)
     m._freeze_clip_parameters()
     assert not m._full_finetune()
-
-
-def test_attention_key_range_pipeline_protocol():
-    """csrc/attention_kr.cu (experimental single-launch attention for ViT-L/14): the mbarrier protocol of its roles,
-    restated in tools/kr_protocol_sim.py, survives random interleavings without deadlock, parity aliasing or a
-    resource being overwritten under a reader - and the single-stage plan the launcher refuses does deadlock."""
-    import importlib.util
-    import random
-
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "kr_protocol_sim.py")
-    spec = importlib.util.spec_from_file_location("kr_protocol_sim", path)
-    sim = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(sim)
-    rng = random.Random(1)
-    for n_units, mtiles, nstage, n_tail in [(1, 1, 2, 0), (3, 2, 2, 1), (5, 2, 3, 1), (4, 3, 2, 0), (8, 1, 3, 1)]:
-        for _ in range(10):
-            sim.simulate(n_units, mtiles, nstage, n_tail, rng)
-    with pytest.raises(AssertionError, match="deadlock"):
-        sim.simulate(2, 1, 1, 0, rng)

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "vlmclip_attn1q_f32_bwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p]),
     "vlmclip_transpose_to_bf16": (_i, [_p, _i, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "vlmclip_cast_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
+    "vlmclip_add_bf16_into_f32": (_i, [_p, _p, _i64, _p]),
     "vlmclip_rowsum_bf16": (_i, [_p, _i64, _p, _i, _i, _p]),
     "vlmclip_colsum_f32": (_i, [_p, _i64, _p, _i, _i64, _p]),
     "vlmclip_quick_gelu_bf16": (_i, [_p, _p, _i64, _p]),

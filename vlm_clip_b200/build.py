@@ -21,7 +21,7 @@ LIBDIR = PKG / "lib"
 OBJDIR = PKG / "build"
 LIB = LIBDIR / "libvlmclip_b200.so"
 
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "attention_pp.cu", "attention_kr.cu", "attention_1q.cu", "encoder.cu", "preprocess.cu", "adapter.cu", "heads.cu", "clip_loss.cu", "optim.cu", "backward.cu",
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "attention_pp.cu", "attention_1q.cu", "encoder.cu", "preprocess.cu", "adapter.cu", "heads.cu", "clip_loss.cu", "optim.cu", "backward.cu",
            "attention_bwd.cu", "attention_bwd_mma.cu", "shared_adapter.cu"]
 
 NVCC_FLAGS = [

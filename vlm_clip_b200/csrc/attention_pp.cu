@@ -9,8 +9,13 @@
 // delivers about 64 B/clk/SM, so S is streamed from TMEM exactly once (a 208-score row does not fit one thread's
 // registers) with the exp2 work hidden behind nothing but the other warpgroup's tile.
 //   warp 0     TMA: per unit Q [128*mtiles x 64], K [Npad x 64], V [Npad x 64] (rows of the fused qkv activation, SW128)
-//   warp 1     tcgen05: S = Q K^T (SS MMA, M=128, N=Npad, 4 k-steps) -> TMEM buffer t&1, issued right behind P.V(t-2);
-//              O = P V (TS MMA: A = P from TMEM, B = V as an MN-major smem operand) -> TMEM columns [448, 512)
+//   warp 1     tcgen05: S = Q K^T (SS MMA, M=128, 4 k-steps) -> TMEM buffer t&1; O = P V (TS MMA: A = P from TMEM, B = V as an
+//              MN-major smem operand) -> TMEM columns [448, 512).  With more than 128 keys S is issued in two parts, keys
+//              [128, Npad) ("hi") and [0, 128) ("lo"), interleaved with the two halves of P.V(t-2) that free the columns
+//              they overwrite: P.V_hi(t-2), S_hi(t), P.V_lo(t-2), S_lo(t).  The softmax warpgroup starts on S_hi after a
+//              fifth of the tensor work it used to wait for (both P.V and the whole S), and S_lo is complete long before
+//              it gets there.  P(t) is written over the first 16 columns of each 32-column S chunk (not compacted at the
+//              front), so that a chunk's P lives inside the column range its own half of S owns.
 //   warps 4-11 softmax, ONE thread per query row, no cross-thread exchange, ONE pass over S: the reference exponent is the
 //              maximum of the row's first chunk (raised by whole octaves, exactly, if a later chunk ever exceeds it by
 //              2^16), p = exp2(s*c - ref) truncated to bf16 with integer ops (F2FP shares the SFU pipe with MUFU.EX2),
@@ -48,6 +53,7 @@ struct PPParams {
   float scale_log2e;
   int Npad;    // keys rounded up to a multiple of 16
   int nb;      // TMEM columns per S buffer: Npad rounded up to 32
+  int n_lo;    // keys [0, n_lo) form the "lo" part of S, [n_lo, Npad) the "hi" part (n_lo = Npad: no split)
   int mtiles;  // query tiles per unit (1 or 2)
   int num_units;
   uint32_t q_bytes;      // mtiles * 16 KB
@@ -147,9 +153,10 @@ __device__ __forceinline__ void exp_chunk(const PPParams& p, const uint32_t (&cu
 // One 32-column chunk of the single-pass softmax: chunk maximum -> (rarely) raise the reference by whole octaves and
 // rescale what was already produced -> exp2 / truncate / sum / pack / store.
 template <bool GENERAL_MASK>
-__device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t (&cur)[32], int ch, int kmax_warp,
-                                              const uint8_t* km, int qrow, float c, float& off, bool& has_ref,
-                                              float (&l4)[4], uint32_t tb) {
+__device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t (&cur)[32], int ch, int ch_first, int nch,
+                                              int kmax_warp, const uint8_t* km, int qrow, float c, float& off,
+                                              bool& has_ref, float (&l4)[4], uint32_t tb) {
+  // chunks are processed in the order ch_first, ..., nch - 1, 0, ..., ch_first - 1 (hi part of S first, see the kernel)
   const int k0 = ch * 32;
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   max_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, m4);
@@ -164,9 +171,12 @@ __device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t 
     const float d = need ? ceilf(excess) : 0.f;
     const float f = exp2f(-d);  // exact power of two
     tmem_wait_st();
-    for (int j = 0; j < ch; ++j) {
+    for (int j = 0; j < nch; ++j) {
+      // already processed: in the hi phase (ch >= ch_first) the chunks [ch_first, ch), in the lo phase those and [0, ch)
+      const bool done = ch >= ch_first ? (j >= ch_first && j < ch) : (j >= ch_first || j < ch);
+      if (!done) continue;
       uint32_t pk[16];
-      tmem_ld_32x32b_x16(tb + j * 16, pk);
+      tmem_ld_32x32b_x16(tb + j * 32, pk);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -174,13 +184,13 @@ __device__ __forceinline__ void softmax_chunk(const PPParams& p, const uint32_t 
         const uint32_t hi = __float_as_uint(__uint_as_float(pk[i] & 0xffff0000u) * f) & 0xffff0000u;
         pk[i] = __byte_perm(lo, hi, 0x7632);
       }
-      tmem_st_32x32b_x16(tb + j * 16, pk);
+      tmem_st_32x32b_x16(tb + j * 32, pk);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) l4[i] *= f;
     off += d;
   }
-  exp_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, c, off, l4, tb + ch * 16);
+  exp_chunk<GENERAL_MASK>(p, cur, k0, kmax_warp, km, qrow, c, off, l4, tb + ch * 32);
 }
 
 // SPLIT: role of the launch in a two-launch key-range split (PPParams::stats / merge), compiled per role so that the
@@ -195,13 +205,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * p.stage_bytes);
   uint64_t* kv_full = bars;                     // [4] TMA landed Q, K, V of a unit
   uint64_t* kv_empty = bars + PP_MAX_STAGES;    // [4] the unit's last P.V finished reading the stage
-  uint64_t* s_full = bars + 2 * PP_MAX_STAGES;  // [2] S = Q K^T complete (per buffer / warpgroup)
+  uint64_t* s_full = bars + 2 * PP_MAX_STAGES;  // [2] the lo part of S = Q K^T (all of it without a split) is complete
   uint64_t* p_full = s_full + 2;                // [2] softmax wrote P (128 arrivals)
   uint64_t* e_done = s_full + 4;                // [2] the epilogue has read the row sums of the buffer (128 arrivals)
   uint64_t* o_full = s_full + 6;                // [1] O = P V complete, in tile order
   uint64_t* o_free = s_full + 7;                // [1] O drained to registers (128 arrivals), in tile order
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
-  float* s_l = reinterpret_cast<float*>(s_full + 10);  // [2][128] row sums, softmax -> epilogue
+  uint64_t* s_hi_full = s_full + 8;             // [2] the hi part of S is complete (only used with a split)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+  float* s_l = reinterpret_cast<float*>(s_full + 12);  // [2][128] row sums, softmax -> epilogue
   float* s_off = s_l + 256;                            // [2][128] reference exponents (key-range split only)
   uint8_t* s_out = smem + p.out_stage_off;             // [128 rows][128 B] bf16 O tile, 16-B chunks XOR-swizzled by row
 
@@ -218,6 +229,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
+      mbar_init(&s_hi_full[b], 1);
       mbar_init(&p_full[b], 128);
       mbar_init(&e_done[b], 128);
     }
@@ -264,24 +276,34 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc_s = make_idesc_bf16(PP_M, p.Npad);
+      const bool split = p.n_lo < p.Npad;
+      const uint32_t idesc_lo = make_idesc_bf16(PP_M, p.n_lo);
+      const uint32_t idesc_hi = make_idesc_bf16(PP_M, split ? p.Npad - p.n_lo : 16);
       const uint32_t idesc_o = make_idesc_bf16_b_mn(PP_M, PP_HD);
       const int ksteps = p.Npad >> 4;
-      auto issue_s = [&](int t) {
+      const int ksteps_lo = p.n_lo >> 4;
+      // S(t), keys [key_b, key_b + N): K rows start key_b * 128 B into the K tile, columns start at key_b of the buffer
+      auto issue_s_part = [&](int t, uint32_t idesc, int key_b, uint64_t* done_bar) {
         const int u = t / p.mtiles, mt = t - u * p.mtiles;
         const int sg = u % p.nstage;
         uint8_t* st = stage0 + sg * p.stage_bytes;
         mbar_wait(&kv_full[sg], (u / p.nstage) & 1);
         tcgen05_fence_after();
         const uint64_t qd = make_umma_desc_sw128(smem_u32(st + mt * PP_Q_TILE_BYTES));
-        const uint64_t kd = make_umma_desc_sw128(smem_u32(st + p.q_bytes));
+        const uint64_t kd = make_umma_desc_sw128(smem_u32(st + p.q_bytes + key_b * 128));
 #pragma unroll
         for (int k = 0; k < PP_HD / 16; ++k)
-          umma_bf16_ss(tmem_base + (t & 1) * p.nb, qd + 2u * k, kd + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[t & 1]);
+          umma_bf16_ss(tmem_base + (t & 1) * p.nb + key_b, qd + 2u * k, kd + 2u * k, idesc, k != 0 ? 1u : 0u);
+        umma_commit(done_bar);
       };
-      if (n_tiles > 0) issue_s(0);
-      if (n_tiles > 1) issue_s(1);
+      auto issue_s_hi = [&](int t) {
+        if (split) issue_s_part(t, idesc_hi, p.n_lo, &s_hi_full[t & 1]);
+      };
+      auto issue_s_lo = [&](int t) { issue_s_part(t, idesc_lo, 0, &s_full[t & 1]); };
+      for (int t = 0; t < 2 && t < n_tiles; ++t) {
+        issue_s_hi(t);
+        issue_s_lo(t);
+      }
       for (int t = 0; t < n_tiles; ++t) {
         const int u = t / p.mtiles, mt = t - u * p.mtiles;
         const int sg = u % p.nstage;
@@ -290,12 +312,18 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(o_free, (t & 1) ^ 1u);          // O(t-1) has been drained
         tcgen05_fence_after();
         const uint64_t vd = make_umma_desc_mn_sw128(smem_u32(st + p.q_bytes + p.kv_stride), p.kv_stride);
-        for (int k = 0; k < ksteps; ++k)  // 16 keys per step: 8 packed TMEM columns of P, 2048 B of V
-          umma_bf16_ts(tmem_base + PP_O_COL, tmem_base + (t & 1) * p.nb + k * 8,
-                       vd + static_cast<uint64_t>(k) * (2048u >> 4), idesc_o, k != 0 ? 1u : 0u);
+        // 16 keys per step: 8 packed TMEM columns of P at the start of the keys' own S chunk half, 2048 B of V.
+        // Key steps of the hi part first: they free the columns S_hi(t+2) overwrites.
+        auto pv = [&](int k, uint32_t acc) {
+          umma_bf16_ts(tmem_base + PP_O_COL, tmem_base + (t & 1) * p.nb + (k >> 1) * 32 + (k & 1) * 8,
+                       vd + static_cast<uint64_t>(k) * (2048u >> 4), idesc_o, acc);
+        };
+        for (int k = ksteps_lo; k < ksteps; ++k) pv(k, k != ksteps_lo ? 1u : 0u);
+        if (t + 2 < n_tiles) issue_s_hi(t + 2);  // in order behind P.V_hi(t): overwrites columns [n_lo, Npad) of buffer t & 1
+        for (int k = 0; k < ksteps_lo; ++k) pv(k, (split || k != 0) ? 1u : 0u);
         umma_commit(o_full);
         if (mt == p.mtiles - 1) umma_commit(&kv_empty[sg]);
-        if (t + 2 < n_tiles) issue_s(t + 2);  // in order behind P.V(t): may overwrite S/P buffer t & 1
+        if (t + 2 < n_tiles) issue_s_lo(t + 2);  // in order behind P.V_lo(t): overwrites columns [0, n_lo)
       }
     }
   }
@@ -515,13 +543,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int kmax_warp = p.causal ? min(p.Sk, mt * PP_M + wq * 32 + 32) : p.Sk;  // keys any row of this warp sees
       const uint32_t par = (t >> 1) & 1;
 
-      mbar_wait(&s_full[wg], par);
+      const int ch_first = p.n_lo < p.Npad ? (p.n_lo >> 5) : 0;  // first chunk of the hi part of S (0: no split)
+      mbar_wait(ch_first > 0 ? &s_hi_full[wg] : &s_full[wg], par);
       tcgen05_fence_after();
       if (dbg) { long long x = clock64(); tk[0] += x - t0; t0 = x; }
       float l = 0.f;
       float off_pub = 0.f;
-      if (warp_valid) {
-        __syncwarp();
+      {
         // ---- single pass over S (TMEM reads are the scarce resource: ~64 B/clk/SM): softmax is shift invariant, so the
         // reference `off` only has to keep exp2 in range.  It starts as the maximum of the row's first visible chunk and
         // is raised by an INTEGER number of octaves (exact rescale of the P already written and of the row sum) only
@@ -530,26 +558,37 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float off = 0.f;
         bool has_ref = false;
         uint32_t sa[32], sb[32];
-        tmem_ld_32x32b_x32(tb, sa);
-        for (int ch = 0; ch < nch; ch += 2) {
-          long long w0 = dbgw ? clock64() : 0;
-          tmem_wait_ld();
-          if (ch + 1 < nch) tmem_ld_32x32b_x32(tb + (ch + 1) * 32, sb);
-          long long w1 = dbgw ? clock64() : 0;
-          softmax_chunk<GENERAL_MASK>(p, sa, ch, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
-          long long w2 = dbgw ? clock64() : 0;
-          tw[0] += w1 - w0;
-          tw[1] += w2 - w1;
-          if (ch + 1 < nch) {
+        // chunks [c0, c1) with the next chunk's tcgen05.ld in flight under the current chunk's arithmetic
+        auto run_chunks = [&](int c0, int c1) {
+          if (!warp_valid || c0 >= c1) return;
+          __syncwarp();
+          tmem_ld_32x32b_x32(tb + c0 * 32, sa);
+          for (int ch = c0; ch < c1; ch += 2) {
+            long long w0 = dbgw ? clock64() : 0;
             tmem_wait_ld();
-            if (ch + 2 < nch) tmem_ld_32x32b_x32(tb + (ch + 2) * 32, sa);
-            long long w3 = dbgw ? clock64() : 0;
-            softmax_chunk<GENERAL_MASK>(p, sb, ch + 1, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
-            long long w4 = dbgw ? clock64() : 0;
-            tw[0] += w3 - w2;
-            tw[1] += w4 - w3;
+            if (ch + 1 < c1) tmem_ld_32x32b_x32(tb + (ch + 1) * 32, sb);
+            long long w1 = dbgw ? clock64() : 0;
+            softmax_chunk<GENERAL_MASK>(p, sa, ch, ch_first, nch, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
+            long long w2 = dbgw ? clock64() : 0;
+            tw[0] += w1 - w0;
+            tw[1] += w2 - w1;
+            if (ch + 1 < c1) {
+              tmem_wait_ld();
+              if (ch + 2 < c1) tmem_ld_32x32b_x32(tb + (ch + 2) * 32, sa);
+              long long w3 = dbgw ? clock64() : 0;
+              softmax_chunk<GENERAL_MASK>(p, sb, ch + 1, ch_first, nch, kmax_warp, km, qrow, c, off, has_ref, l4, tb);
+              long long w4 = dbgw ? clock64() : 0;
+              tw[0] += w3 - w2;
+              tw[1] += w4 - w3;
+            }
           }
+        };
+        if (ch_first > 0) {
+          run_chunks(ch_first, nch);       // hi part: available after P.V_hi(t-2) + S_hi(t) only
+          mbar_wait(&s_full[wg], par);     // lo part: issued behind P.V_lo(t-2), long complete by now
+          tcgen05_fence_after();
         }
+        run_chunks(0, ch_first > 0 ? ch_first : nch);
         l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         off_pub = off;
       }
@@ -613,6 +652,14 @@ int launch_range(const void* qkv, void* out, const uint8_t* key_mask, int B, int
   p.stats = stats;
   p.Npad = (Sk + 15) / 16 * 16;
   p.nb = (p.Npad + 31) / 32 * 32;
+  {
+    // S in two parts when there are more than 128 keys (VLMCLIP_ATTN_SSPLIT=0 issues it whole, for A/B measurements)
+    static const bool ssplit = []() {
+      const char* e = getenv("VLMCLIP_ATTN_SSPLIT");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    p.n_lo = (ssplit && p.Npad > 128) ? 128 : p.Npad;
+  }
   p.mtiles = (Sq + PP_M - 1) / PP_M;
   p.q_loads = p.mtiles <= 2 ? 1 : p.mtiles;
   p.num_units = B * H;
@@ -626,7 +673,7 @@ int launch_range(const void* qkv, void* out, const uint8_t* key_mask, int B, int
   }
   int nstage = (int)((206u * 1024u) / p.stage_bytes);  // 227 KB - 16 KB output tile - barriers / row sums / exponents
   p.nstage = nstage < 2 ? 2 : (nstage > PP_MAX_STAGES ? PP_MAX_STAGES : nstage);
-  const size_t ctrl = (2 * PP_MAX_STAGES + 10) * 8 + 512 * sizeof(float) + 16;
+  const size_t ctrl = (2 * PP_MAX_STAGES + 12) * 8 + 512 * sizeof(float) + 16;
   p.out_stage_off = (uint32_t)(((size_t)p.nstage * p.stage_bytes + ctrl + 1023) & ~(size_t)1023);
   const size_t smem = (size_t)p.out_stage_off + PP_M * 128;
   if (smem > 232448) {

@@ -17,20 +17,17 @@ int attention_fwd_pingpong(const void* qkv, void* out, const uint8_t* key_mask, 
                            cudaStream_t stream);
 int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, int B, int S, int H, float scale,
                                  int variant, cudaStream_t stream);
-int attention_fwd_keyranges(const void* qkv, void* out, int B, int S, int H, float scale, cudaStream_t stream);
-bool attention_keyranges_supported(int S);
 
 }  // namespace vlmclip
 
 using namespace vlmclip;
 
 // VLMCLIP_ATTN_SPLIT: 0 keeps S > 224 on the mma.sync kernel, 1 / 2 / 3 select the variant of the key-range split
-// (attention_pp.cu: attention_fwd_pingpong_split), 4 the single-launch kernel of attention_kr.cu (EXPERIMENTAL: not yet
-// run on a GPU, never selected by default); A/B switch, read once
+// (attention_pp.cu: attention_fwd_pingpong_split); A/B switch, read once
 static int split_variant() {
   static const int variant = []() {
     const char* e = getenv("VLMCLIP_ATTN_SPLIT");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
   }();
   return variant;
 }
@@ -60,9 +57,6 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
     const char* e = getenv("VLMCLIP_ATTN_FORCE_TC");
     return e != nullptr && e[0] == '1';
   }();
-  if (workspace != nullptr && split_eligible(S, causal, key_mask) && split_variant() == 4 &&
-      attention_keyranges_supported(S))
-    return attention_fwd_keyranges(qkv, out, B, S, H, scale, s);
   if (workspace != nullptr && split_eligible(S, causal, key_mask))
     return attention_fwd_pingpong_split(qkv, out, workspace, B, S, H, scale, split_variant(), s);
   if (S > 224 || (!force_tc && (causal != 0 || key_mask != nullptr) && S <= 128))

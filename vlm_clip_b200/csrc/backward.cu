@@ -139,6 +139,13 @@ cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
   }
 }
 
+// acc[i] += float(b[i]): a bf16 gradient branch joins the fp32 gradient of a skip connection
+__global__ void __launch_bounds__(256)
+add_bf16_into_f32_kernel(float* __restrict__ acc, const __nv_bfloat16* __restrict__ b, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) acc[i] += __bfloat162float(b[i]);
+}
+
 // out[r] = sum_c x[r, c]: one CTA per row (rows are long: the token dimension of a transposed gradient)
 __global__ void __launch_bounds__(256)
 rowsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ out, int C) {
@@ -443,6 +450,13 @@ extern "C" int vlmclip_cast_f32_to_bf16(const float* src, void* dst, int64_t n, 
   cast_f32_to_bf16_kernel<<<grid_cap((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n,
                                                                                        vec_ok);
   return report_cuda(cudaGetLastError(), "cast_f32_to_bf16_kernel launch");
+}
+
+extern "C" int vlmclip_add_bf16_into_f32(float* acc, const void* b, int64_t n, void* stream) {
+  VLMCLIP_CHECK_ARG(acc && b && n > 0, "add_bf16_into_f32: bad arguments");
+  count_launch(1);
+  add_bf16_into_f32_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)b, n);
+  return report_cuda(cudaGetLastError(), "add_bf16_into_f32_kernel launch");
 }
 
 extern "C" int vlmclip_rowsum_bf16(const void* x, int64_t ldx, float* out, int R, int C, void* stream) {

@@ -29,7 +29,7 @@ import torch.nn as nn
 from . import _native as N
 from . import ops
 from .adapter.clip_adapter import SharedMHSAttentionAdapter, TextAdapter, VisionAdapter
-from .adapter.peclip import TextualAdapter
+from .adapter.peclip import ContextAdapter, TextualAdapter
 from .constants import CLIP_MEAN, CLIP_STD
 from .finetune import TrainableClipTowers, linear_f32_trainable
 from .towers import NativeClipTowers
@@ -86,15 +86,22 @@ class CLIPWithAdapters(nn.Module):
         self.shared_adapters = None
         # `adapter_kind` is an extension (BASELINE config 3): "peclip" puts adapter/peclip.py's TextualAdapter
         # (up(gelu(down x)) + x, no LayerNorm) into the same two slots; the reference wires PE-CLIP adapters into no model.
-        if adapter_kind not in ("clip_adapter", "peclip"):
-            raise ValueError(f"adapter_kind must be 'clip_adapter' or 'peclip', got {adapter_kind!r}")
+        # "peclip_context" puts peclip.ContextAdapter (LayerNorm(MHSA(x) + x) over the image patches, adapter/peclip.py:21-34)
+        # into the vision slot and TextualAdapter into the text slot: the PE-CLIP pairing of a textual bottleneck with a
+        # spatial-context adapter.  It mixes tokens, so it runs on the whole [B, S, D] stream before the CLS row is taken.
+        if adapter_kind not in ("clip_adapter", "peclip", "peclip_context"):
+            raise ValueError(f"adapter_kind must be 'clip_adapter', 'peclip' or 'peclip_context', got {adapter_kind!r}")
         self.adapter_kind = adapter_kind
         if self.use_text_adapter:
             self.text_adapter = (TextAdapter(text_hidden_size, text_adapter_size) if adapter_kind == "clip_adapter"
                                  else TextualAdapter(text_hidden_size, text_adapter_size))
         if self.use_vision_adapter:
-            self.vision_adapter = (VisionAdapter(vision_hidden_size, vision_adapter_size) if adapter_kind == "clip_adapter"
-                                   else TextualAdapter(vision_hidden_size, vision_adapter_size))
+            if adapter_kind == "clip_adapter":
+                self.vision_adapter = VisionAdapter(vision_hidden_size, vision_adapter_size)
+            elif adapter_kind == "peclip":
+                self.vision_adapter = TextualAdapter(vision_hidden_size, vision_adapter_size)
+            else:
+                self.vision_adapter = ContextAdapter(vision_hidden_size, self.clip.vision_model.config.num_attention_heads)
         if self.use_shared_adapters:
             self.shared_adapters = nn.ModuleList(
                 [SharedMHSAttentionAdapter(text_hidden_size, vision_hidden_size) for _ in range(shared_adapter_layers)])
@@ -261,15 +268,31 @@ class CLIPWithAdapters(nn.Module):
             pixel_values = pixel_values.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
         return bb.vision_stream(pixel_values, cls_only), pixel_values.shape[0], seq
 
+    def _vision_adapter_mixes_tokens(self) -> bool:
+        return self.use_vision_adapter and isinstance(self.vision_adapter, ContextAdapter)
+
+    def _image_rows(self, bb, hidden, n, seq):
+        """What the trainable half reads from the vision tower: the fp32 CLS rows [n, Dv] (hi + lo of the residual stream),
+        or the whole bf16 stream [n, S, Dv] when the vision adapter mixes tokens."""
+        if self._vision_adapter_mixes_tokens():
+            if seq != bb.Sv:
+                raise N.NativeError("vision_cls_only_last_layer cannot be combined with a token-mixing vision adapter")
+            return hidden.hi.view(n, seq, bb.Dv)
+        return hidden.rows_f32(n, seq * bb.Dv, bb.Dv)
+
     def _image_head(self, bb, hidden, B, seq=None):
         seq = bb.Sv if seq is None else seq
-        return self._image_head_rows(bb, hidden.rows_f32(B, seq * bb.Dv, bb.Dv))
+        return self._image_head_rows(bb, self._image_rows(bb, hidden, B, seq))
 
     def _image_head_rows(self, bb, cls):
         """cls: fp32 [n, Dv] = the CLS rows (hi + lo of the residual stream).  The adapter is position-wise, so evaluating
         it on row 0 of every sequence is result-identical to the reference's all-token call followed by [:, 0, :]
         (model_m.py:116-122)."""
-        if self.use_vision_adapter:
+        if cls.dim() == 3:
+            # token-mixing vision adapter (ContextAdapter): cls is the whole bf16 stream [n, S, Dv]; the reference's order
+            # is adapter on all tokens, then [:, 0, :] (model_m.py:116-122)
+            cls = self.vision_adapter(cls)[:, 0, :].contiguous()
+        elif self.use_vision_adapter:
             cls = self.vision_adapter(cls)
         return ops.linear_f32(cls, bb.visual_projection)
 
@@ -336,7 +359,7 @@ class CLIPWithAdapters(nn.Module):
             v_hidden, n_img, v_seq = self._vision_hidden(bb, pixel_values)
         S = 1 if (self.text_token0_only and input_ids.shape[1] > 1) else input_ids.shape[1]
         rows_t = t_hidden.rows_f32(input_ids.shape[0], S * bb.Dt, bb.Dt)
-        rows_v = v_hidden.rows_f32(n_img, v_seq * bb.Dv, bb.Dv)
+        rows_v = self._image_rows(bb, v_hidden, n_img, v_seq)
         return rows_t, rows_v
 
     def features_from_pooled(self, rows_t, rows_v):

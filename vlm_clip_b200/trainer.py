@@ -159,6 +159,9 @@ class CLIPAdapterTrainer:
         of enqueueing ~230 kernels through the interpreter, which is what made the end-to-end rate depend on the host
         (14.6 vs 11.7 ms per step on a slow box)."""
         device = next(self.model.parameters()).device
+        # the optimiser is created on first use and, under data parallelism, broadcasts rank 0's parameters: that must
+        # happen BEFORE the first forward, or step 0 runs each rank on its own initialisation
+        self.optimizer  # noqa: B018
         batch = {k: v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
         if self.cuda_graph and self._graphable(batch):
             loss = self._graphed_step(batch)
@@ -261,6 +264,16 @@ class CLIPAdapterTrainer:
         # capture only records: the effects of a step (optimizer update, Adam step counter) happen on replay
         st["copied"].record(main)
         st["G_T"], st["G_H"] = g_t, g_h
+
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (and their private memory pools).  Call before tearing down a process group
+        whose collectives were captured: NCCL cannot destroy a communicator while graphs holding its kernels exist."""
+        import gc
+
+        self._graphs.clear()
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def train(self, num_epochs, save_every=1, eval_every=1):
         from tqdm import tqdm
