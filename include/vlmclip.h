@@ -64,13 +64,18 @@ int64_t vlmclip_launch_count(void);
  *   sum (x - mean)^2) of each 32-column block of the row, combined in the epilogue (Chan) with eps = ln_eps.
  *   stats_part_out (optional, bf16 output, N % 32 == 0): the epilogue writes those partials for the rows it
  *   produces, fp32 [M][N/32][2], so the next LN-folded layer needs no separate statistics pass over HBM.
+ *   stats_out + row_counters (optional, with stats_part_out): the CTA that completes the last column tile of a 128-row
+ *   block also combines that block's partials into (mean, rstd) rows of stats_out fp32 [M][2] (eps = ln_eps), which
+ *   replaces a vlmclip_ln_partials_to_stats launch.  row_counters: ceil(M / 128) 32-bit words, ZERO before the first
+ *   call; every launch leaves them zero (one buffer per stream can be reused for ever).
  *   C: bf16 (out_fp32 = 0) or fp32 (out_fp32 = 1).  K % 8 == 0, N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0,
  *   16-byte aligned base pointers.
  * --------------------------------------------------------------------------------------------------------- */
 int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                       const float* bias, const void* residual, int64_t ldr, const float* row_stats,
                       const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
-                      float* stats_part_out, int M, int N, int K, int act, int out_fp32, void* stream);
+                      float* stats_part_out, float* stats_out, int32_t* row_counters, int M, int N, int K, int act,
+                      int out_fp32, void* stream);
 /* Two-term residual update of an encoder layer (HF modeling_clip.py:372-373, 382-383 `hidden_states = residual +
  * hidden_states`), in place:  x += A[M,K] * W[N,K]^T + bias, where the residual stream x is stored as TWO bf16 planes,
  * hi = bf16(x) at X and lo = bf16(x - hi) at X + plane_stride elements (both [M, N], leading dimension ldx).  hi is
@@ -79,8 +84,8 @@ int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
  * set by the bf16 operand roundings any bf16 execution has).  stats_part_out as in vlmclip_gemm_bf16, computed from
  * the fp32 values before they are split. */
 int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
-                           int64_t plane_stride, const float* bias, float* stats_part_out, int M, int N, int K,
-                           void* stream);
+                           int64_t plane_stride, const float* bias, float* stats_part_out, float* stats_out,
+                           int32_t* row_counters, float ln_eps, int M, int N, int K, void* stream);
 
 /* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */
@@ -173,9 +178,11 @@ typedef struct {
 } vlmclip_layer_t;
 /* x_lo (optional): second plane of the two-term residual stream, bf16 [B*S, D] (see vlmclip_gemm_bf16_res2); NULL keeps
  * the stream in one bf16 plane (half the residual traffic, 2.5x the end-to-end rounding error). */
+/* row_counters (optional): ceil(B*S / 128) zeroed 32-bit words (see vlmclip_gemm_bf16); with them the out-proj / fc2
+ * epilogues finalise the LayerNorm statistics themselves and the 2 L - 1 ln_partials_to_stats launches disappear. */
 int vlmclip_encoder_fwd(const vlmclip_layer_t* layers, int n_layers, void* x, void* x_lo, void* qkv, void* att, void* hid,
-                        float* stats, float* part, const uint8_t* key_mask, int B, int S, int H, int D, int F, float eps,
-                        int causal, int act, void* stream);
+                        float* stats, float* part, int32_t* row_counters, const uint8_t* key_mask, int B, int S, int H,
+                        int D, int F, float eps, int causal, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused bottleneck adapter, fp32 (trainable weights live in fp32; adapter/clip_adapter.py:4-23,131-150,

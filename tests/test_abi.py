@@ -55,7 +55,7 @@ def test_abi_version_and_error_channel(lib):
     assert isinstance(lib.vlmclip_last_error(), bytes)
     assert lib.vlmclip_launch_count() >= 0
     # argument validation happens before any CUDA call, so it can be exercised without a GPU
-    rc = lib.vlmclip_gemm_bf16(None, 0, None, 0, None, 0, None, None, 0, None, None, None, 0, 1e-5, None, 1, 1, 1, 0, 0, None)
+    rc = lib.vlmclip_gemm_bf16(None, 0, None, 0, None, 0, None, None, 0, None, None, None, 0, 1e-5, None, None, None, 1, 1, 1, 0, 0, None)
     assert rc < 0 and b"null" in lib.vlmclip_last_error()
     assert lib.vlmclip_adapter_bwd_workspace(5, 768, 256) == 8 * (3 * 768 + 2 * 256)
     assert lib.vlmclip_clip_loss_workspace(256, 512) == 4 * 256 + 256 * 256 + 2 * 256 * 512

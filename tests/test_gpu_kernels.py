@@ -157,6 +157,46 @@ def test_gemm_res2_two_term_residual(cuda, M, N, K, cfg, monkeypatch):
     assert torch.allclose(part[..., 1], ref_m2, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K,two_term", [(1000, 768, 768, True), (6304, 768, 3072, True), (2048, 512, 2048, True),
+                                             (771, 1024, 1024, False), (100, 768, 768, True), (50432, 768, 768, True)])
+def test_residual_gemm_finalises_layernorm_statistics(cuda, M, N, K, two_term):
+    """Fused LayerNorm statistics: the CTA that completes the last column tile of a 128-row block combines the block's
+    (mean, M2) partials into (mean, rstd) rows - must equal the separate ln_partials_to_stats pass and the statistics of
+    the fp32 result, for both residual epilogues, and leave the row-block counters zero for the next launch."""
+    from vlm_clip_b200 import ops
+
+    g = _gen(M + N + K + int(two_term))
+    a = torch.randn(M, K, device=cuda, generator=g).to(bf16)
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).to(bf16)
+    bias = torch.randn(N, device=cuda, generator=g)
+    x = torch.randn(M, N, device=cuda, generator=g) * 2 + 0.7
+    part = torch.zeros(M, N // 32, 2, device=cuda)
+    stats = torch.full((M, 2), float("nan"), device=cuda)
+    counters = torch.zeros((M + 127) // 128, device=cuda, dtype=torch.int32)
+    for rep in range(2):  # second launch: the counters must have been left at zero
+        stats.fill_(float("nan"))
+        if two_term:
+            x2 = torch.empty(2, M, N, device=cuda, dtype=bf16)
+            x2[0] = x.to(bf16)
+            x2[1] = (x - x2[0].float()).to(bf16)
+            ref = a.float() @ w.float().t() + bias + x2[0].float() + x2[1].float()
+            ops.gemm_res2(a, w, bias, x2, stats_part_out=part, stats_out=stats, row_counters=counters, ln_eps=1e-5)
+        else:
+            xb = x.to(bf16)
+            ref = a.float() @ w.float().t() + bias + xb.float()
+            ops.gemm(a, w, bias=bias, residual=xb, out=xb, stats_part_out=part, stats_out=stats, row_counters=counters,
+                     ln_eps=1e-5)
+        torch.cuda.synchronize()
+        assert int(counters.abs().sum().item()) == 0
+        sep = ops.ln_partials_to_stats(part, 1e-5)
+        assert torch.isfinite(stats).all()
+        assert torch.allclose(stats, sep, rtol=1e-5, atol=1e-6)
+        mu = ref.mean(-1)
+        rstd = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
+        assert torch.allclose(stats[:, 0], mu, atol=2e-5, rtol=1e-5)
+        assert torch.allclose(stats[:, 1], rstd, atol=1e-6, rtol=1e-4)
+
+
 def test_gemm_res2_rejects_overlapping_planes(cuda):
     from vlm_clip_b200 import _native as N
 
@@ -164,7 +204,8 @@ def test_gemm_res2_rejects_overlapping_planes(cuda):
     w = torch.zeros(256, 64, device=cuda, dtype=bf16)
     x = torch.zeros(2 * 256 * 256, device=cuda, dtype=bf16)
     b = torch.zeros(256, device=cuda)
-    rc = N.load().vlmclip_gemm_bf16_res2(N.ptr(a), 64, N.ptr(w), 64, N.ptr(x), 256, 128, N.ptr(b), None, 256, 256, 64, N.stream())
+    rc = N.load().vlmclip_gemm_bf16_res2(N.ptr(a), 64, N.ptr(w), 64, N.ptr(x), 256, 128, N.ptr(b), None, None, None, 1e-5,
+                                         256, 256, 64, N.stream())
     assert rc < 0 and b"overlap" in N.load().vlmclip_last_error()
 
 

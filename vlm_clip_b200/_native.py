@@ -25,8 +25,8 @@ PROTOTYPES = {
     "vlmclip_abi_version": (_i, []),
     "vlmclip_last_error": (C.c_char_p, []),
     "vlmclip_launch_count": (_i64, []),
-    "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _i, _f, _p, _i, _i, _i, _i, _i, _p]),
-    "vlmclip_gemm_bf16_res2": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _i, _i, _i, _p]),
+    "vlmclip_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _p, _p, _i, _f, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vlmclip_gemm_bf16_res2": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _f, _i, _i, _i, _p]),
     "vlmclip_layernorm_bf16": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_layernorm_bf16_f32out": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _f, _p]),
     "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),
@@ -41,7 +41,7 @@ PROTOTYPES = {
     "vlmclip_attention_fwd_workspace": (_i64, [_i, _i, _i]),
     "vlmclip_attention_fwd_ws": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "vlmclip_attention_1q": (_i, [_p, _i64, _p, _p, _i64, _i64, _p, _i, _i, _i, _f, _p]),
-    "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
+    "vlmclip_encoder_fwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p]),
     "vlmclip_adapter_fwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
     "vlmclip_adapter_bwd_workspace": (_i64, [_i, _i, _i]),
     "vlmclip_adapter_bwd": (_i, [_p, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,

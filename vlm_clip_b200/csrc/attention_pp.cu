@@ -11,11 +11,11 @@
 //   warp 0     TMA: per unit Q [128*mtiles x 64], K [Npad x 64], V [Npad x 64] (rows of the fused qkv activation, SW128)
 //   warp 1     tcgen05: S = Q K^T (SS MMA, M=128, 4 k-steps) -> TMEM buffer t&1; O = P V (TS MMA: A = P from TMEM, B = V as an
 //              MN-major smem operand) -> TMEM columns [448, 512).  With more than 128 keys S is issued in two parts, keys
-//              [128, Npad) ("hi") and [0, 128) ("lo"), interleaved with the two halves of P.V(t-2) that free the columns
-//              they overwrite: P.V_hi(t-2), S_hi(t), P.V_lo(t-2), S_lo(t).  The softmax warpgroup starts on S_hi after a
-//              fifth of the tensor work it used to wait for (both P.V and the whole S), and S_lo is complete long before
-//              it gets there.  P(t) is written over the first 16 columns of each 32-column S chunk (not compacted at the
-//              front), so that a chunk's P lives inside the column range its own half of S owns.
+//              [128, Npad) ("hi") and [0, 128) ("lo"), CAN be interleaved with the two halves of P.V(t-2) that free the
+//              columns they overwrite: P.V_hi(t-2), S_hi(t), P.V_lo(t-2), S_lo(t), so that the softmax warpgroup starts on
+//              S_hi after a fifth of the tensor work it otherwise waits for (VLMCLIP_ATTN_SSPLIT=1; measured slower, see
+//              launch_range, and therefore off).  P(t) is written over the first 16 columns of each 32-column S chunk
+//              (not compacted at the front), so that a chunk's P lives inside the column range its own half of S owns.
 //   warps 4-11 softmax, ONE thread per query row, no cross-thread exchange, ONE pass over S: the reference exponent is the
 //              maximum of the row's first chunk (raised by whole octaves, exactly, if a later chunk ever exceeds it by
 //              2^16), p = exp2(s*c - ref) truncated to bf16 with integer ops (F2FP shares the SFU pipe with MUFU.EX2),
@@ -653,10 +653,14 @@ int launch_range(const void* qkv, void* out, const uint8_t* key_mask, int B, int
   p.Npad = (Sk + 15) / 16 * 16;
   p.nb = (p.Npad + 31) / 32 * 32;
   {
-    // S in two parts when there are more than 128 keys (VLMCLIP_ATTN_SSPLIT=0 issues it whole, for A/B measurements)
+    // S in two parts when there are more than 128 keys: OFF by default.  Measured on B200 (profiles/
+    // r02_attention_s_split_ab.txt, B = 256, S = 197, H = 12): the wait for S drops from 2.9 k to 1.6 k cycles per tile as
+    // intended, but the chunk loop that now runs concurrently with the other half's MMAs slows from 6.0 k to 8.8 k cycles
+    // (TMEM port and issue slots are shared with the tensor pipe's operand reads): 166 us against 132 us.
+    // VLMCLIP_ATTN_SSPLIT=1 enables it for A/B measurements.
     static const bool ssplit = []() {
       const char* e = getenv("VLMCLIP_ATTN_SSPLIT");
-      return !(e != nullptr && e[0] == '0');
+      return e != nullptr && e[0] == '1';
     }();
     p.n_lo = (ssplit && p.Npad > 128) ? 128 : p.Npad;
   }

@@ -52,6 +52,11 @@ struct GemmParams {
   const float* col_c;      // [N]
   const float* part_in;    // [M][npart_in][2] (mean, M2) of 32-column blocks of the A operand's rows (LN fold)
   float* part_out;         // [M][N/32][2] same statistics of the rows this GEMM writes (for the next LN-folded layer)
+  // Fused combine of part_out: the CTA that finishes the LAST column tile of a 128-row block (counted in row_counters,
+  // one zero-initialised word per row block, left zero again) turns the block's partials into (mean, rstd) rows of
+  // stats_out [M][2] - what a separate ln_partials_to_stats launch did (46 launches per ViT-B/16 step).
+  float* stats_out;
+  unsigned* row_counters;
   int npart_in;
   float ln_eps;
   int64_t ldc, ldr;
@@ -176,6 +181,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* res_full_bar = bars + 2 * STAGES + 4;            // [2][EB] panel is free (and holds the residual)
   uint64_t* e_written_bar = bars + 2 * STAGES + 4 + 2 * EB;  // [2][EB] the group has written its result panel
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+  volatile uint32_t* s_last_tile = tmem_slot + 1;  // epilogue: "this CTA completed its row block" (fused LN statistics)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -556,6 +562,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tcgen05_fence_before();
           (PAIR ? mbar_arrive_leader(&tempty_bar[abuf]) : mbar_arrive(&tempty_bar[abuf]));
         }
+        if ((EPI == EPI_RES || EPI == EPI_RES2 || EPI == EPI_GENERIC) && k_part_out && p.stats_out != nullptr) {
+          // ---- fused LayerNorm statistics: last column tile of this 128-row block? ----
+          __threadfence();  // this thread's partials are visible device-wide before the CTA is counted
+          named_bar_sync(2, EPI_THREADS);
+          if (et == 0) {
+            const unsigned old = atomicAdd(&p.row_counters[m_blk], 1u);
+            const bool last = old == (unsigned)(p.n_tiles - 1);
+            if (last) p.row_counters[m_blk] = 0u;  // nobody else touches it any more in this launch
+            *s_last_tile = last ? 1u : 0u;
+          }
+          named_bar_sync(2, EPI_THREADS);
+          if (*s_last_tile != 0u && et < BLOCK_M) {
+            __threadfence();
+            const int r = m_blk * BLOCK_M + et;
+            if (r < p.M) {
+              // Chan's parallel combination of the (mean, M2) partials of the row's 32-column blocks
+              const int np = p.N >> 5;
+              const float2* pp = reinterpret_cast<const float2*>(p.part_out) + (int64_t)r * np;
+              float msum = 0.f;
+              for (int i = 0; i < np; ++i) msum += __ldcg(&pp[i]).x;
+              const float mean = msum / (float)np;
+              float m2 = 0.f;
+              for (int i = 0; i < np; ++i) {
+                const float2 q = __ldcg(&pp[i]);
+                const float d = q.x - mean;
+                m2 += q.y + 32.f * d * d;
+              }
+              reinterpret_cast<float2*>(p.stats_out)[r] = make_float2(mean, rsqrtf(m2 / (32.f * (float)np) + p.ln_eps));
+            }
+          }
+        }
       } else if (EPI == EPI_GENERIC) {
         // ---- direct path (fp32 output): registers -> global ----
 #pragma unroll 1
@@ -668,7 +705,8 @@ using namespace vlmclip;
 extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                  const float* bias, const void* residual, int64_t ldr, const float* row_stats,
                                  const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
-                                 float* stats_part_out, int M, int N, int K, int act, int out_fp32, void* stream) {
+                                 float* stats_part_out, float* stats_out, int32_t* row_counters, int M, int N, int K, int act,
+                                 int out_fp32, void* stream) {
   VLMCLIP_CHECK_ARG(A && W && C, "gemm: null A/W/C pointer");
   VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dims M=%d N=%d K=%d", M, N, K);
   VLMCLIP_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8 (K=%d N=%d)", K, N);
@@ -684,6 +722,8 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
                     "gemm: stats_part_in must hold K/32 = %d partials per row (got %d)", K / 32, npart_in);
   VLMCLIP_CHECK_ARG(stats_part_out == nullptr || (N % 32 == 0 && !out_fp32),
                     "gemm: stats_part_out needs N %% 32 == 0 and bf16 output");
+  VLMCLIP_CHECK_ARG((stats_out == nullptr) == (row_counters == nullptr) && (stats_out == nullptr || stats_part_out != nullptr),
+                    "gemm: stats_out needs row_counters and stats_part_out");
   if (residual) {
     VLMCLIP_CHECK_ARG(ldr % 8 == 0 && ldr >= N && (uintptr_t)residual % 16 == 0,
                       "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
@@ -699,6 +739,8 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.col_c = col_c;
   p.part_in = stats_part_in;
   p.part_out = stats_part_out;
+  p.stats_out = stats_out;
+  p.row_counters = reinterpret_cast<unsigned*>(row_counters);
   p.npart_in = npart_in;
   p.ln_eps = ln_eps;
   p.ldc = ldc;
@@ -801,8 +843,8 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 // x (two planes: hi at X, lo at X + plane_stride) += A W^T + bias, in place; optional LayerNorm partials of the updated
 // rows.  The out-proj / fc2 step of an encoder layer (HF modeling_clip.py:372-383) on the two-term residual stream.
 extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
-                                      int64_t plane_stride, const float* bias, float* stats_part_out, int M, int N, int K,
-                                      void* stream) {
+                                      int64_t plane_stride, const float* bias, float* stats_part_out, float* stats_out,
+                                      int32_t* row_counters, float ln_eps, int M, int N, int K, void* stream) {
   VLMCLIP_CHECK_ARG(A && W && X && bias, "gemm_res2: null A/W/X/bias pointer");
   VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_res2: non-positive dims M=%d N=%d K=%d", M, N, K);
   VLMCLIP_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm_res2: K and N must be multiples of 8 (K=%d N=%d)", K, N);
@@ -814,13 +856,17 @@ extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W,
                         ((uintptr_t)bias % 16 == 0),
                     "gemm_res2: A/W/X/bias must be 16-byte aligned");
   VLMCLIP_CHECK_ARG(stats_part_out == nullptr || N % 32 == 0, "gemm_res2: stats_part_out needs N %% 32 == 0");
+  VLMCLIP_CHECK_ARG((stats_out == nullptr) == (row_counters == nullptr) && (stats_out == nullptr || stats_part_out != nullptr),
+                    "gemm_res2: stats_out needs row_counters and stats_part_out");
 
   GemmParams p{};
   p.C = X;
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(X);
   p.part_out = stats_part_out;
-  p.ln_eps = 0.f;
+  p.stats_out = stats_out;
+  p.row_counters = reinterpret_cast<unsigned*>(row_counters);
+  p.ln_eps = ln_eps;
   p.ldc = ldx;
   p.ldr = ldx;
   p.M = M;

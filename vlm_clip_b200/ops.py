@@ -51,7 +51,7 @@ def _req(cond: bool, msg: str) -> None:
 # --------------------------------------------------------------------------------------------- dense layers
 @_traced
 def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=False, row_stats=None, col_c=None,
-         stats_part_in=None, ln_eps=1e-5, stats_part_out=None):
+         stats_part_in=None, ln_eps=1e-5, stats_part_out=None, stats_out=None, row_counters=None):
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) on tcgen05 tensor cores (vlmclip_gemm_bf16)."""
     _req(a.dtype == bf16 and w.dtype == bf16, "gemm: a and w must be bf16")
     _req(a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1], "gemm: shape mismatch")
@@ -73,8 +73,8 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
         lib.vlmclip_gemm_bf16(
             N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(out), out.stride(0), N.ptr(bias), N.ptr(residual),
             residual.stride(0) if residual is not None else 0, N.ptr(row_stats), N.ptr(col_c), N.ptr(stats_part_in),
-            (K // 32) if stats_part_in is not None else 0, float(ln_eps), N.ptr(stats_part_out), M, Nn, K, int(act),
-            1 if out_fp32 else 0, N.stream()),
+            (K // 32) if stats_part_in is not None else 0, float(ln_eps), N.ptr(stats_part_out), N.ptr(stats_out),
+            N.ptr(row_counters), M, Nn, K, int(act), 1 if out_fp32 else 0, N.stream()),
         "vlmclip_gemm_bf16")
     if prof is not None:
         e1.record()
@@ -83,7 +83,7 @@ def gemm(a, w, bias=None, residual=None, act=N.ACT_NONE, out=None, out_fp32=Fals
 
 
 @_traced
-def gemm_res2(a, w, bias, x2, stats_part_out=None):
+def gemm_res2(a, w, bias, x2, stats_part_out=None, stats_out=None, row_counters=None, ln_eps=1e-5):
     """Two-term residual update in place (vlmclip_gemm_bf16_res2): x2[0] + x2[1] += a[M,K] @ w[N,K]^T + bias, with
     x2 = bf16 [2, M, N] holding hi = bf16(x) and lo = bf16(x - hi).  Returns x2."""
     _req(a.dtype == bf16 and w.dtype == bf16 and x2.dtype == bf16, "gemm_res2: a, w, x2 must be bf16")
@@ -98,7 +98,8 @@ def gemm_res2(a, w, bias, x2, stats_part_out=None):
         e0.record()
     N.check(
         N.load().vlmclip_gemm_bf16_res2(N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(x2), x2.stride(1), x2.stride(0),
-                                        N.ptr(bias), N.ptr(stats_part_out), M, Nn, K, N.stream()),
+                                        N.ptr(bias), N.ptr(stats_part_out), N.ptr(stats_out), N.ptr(row_counters),
+                                        float(ln_eps), M, Nn, K, N.stream()),
         "vlmclip_gemm_bf16_res2")
     if prof is not None:
         e1.record()

@@ -87,6 +87,7 @@ def _pack_layers(sd: Dict[str, torch.Tensor], prefix: str, dev, keep_raw: bool) 
 
 
 _STATS_IN_GEMM = os.environ.get("VLMCLIP_STATS_IN_GEMM", "0") == "1"  # experiment switch
+_FUSED_STATS = os.environ.get("VLMCLIP_FUSED_STATS", "1") != "0"      # residual GEMMs finalise the LN statistics
 
 
 class Hidden:
@@ -182,6 +183,19 @@ class NativeClipTowers:
             self._tables[key] = tab
         return tab
 
+    def _row_counters(self, layers, M: int, dev):
+        """Zeroed int32 words for the fused LayerNorm statistics of the residual GEMMs (one per 128-row block; every
+        launch leaves them zero).  One buffer per tower: the towers run concurrently on two streams.
+        VLMCLIP_FUSED_STATS=0 returns None: separate ln_partials_to_stats launches (A/B switch)."""
+        if not _FUSED_STATS:
+            return None
+        key = ("cnt", id(layers))
+        buf = self._tables.get(key)
+        need = (M + 127) // 128
+        if buf is None or buf.numel() < need or buf.device != dev:
+            buf = self._tables[key] = torch.zeros(max(need, 1024), device=dev, dtype=torch.int32)
+        return buf
+
     def _new_stream(self, M: int, D: int, dev) -> torch.Tensor:
         """Storage of a residual stream: bf16 [P, M, D] with P = 2 planes (hi, lo) for the two-term stream, else 1."""
         return torch.empty((2 if self.residual == "hilo" else 1, M, D), device=dev, dtype=bf16)
@@ -214,8 +228,9 @@ class NativeClipTowers:
                 table = self._layer_table(layers)
                 N.check(
                     N.load().vlmclip_encoder_fwd(table, n_full, N.ptr(x), N.ptr(x_lo), N.ptr(qkv), N.ptr(att), N.ptr(hid),
-                                                 N.ptr(stats), N.ptr(part), N.ptr(key_mask), B, S, H, D, F, float(eps),
-                                                 1 if causal else 0, N.ACT_QUICK_GELU, N.stream()), "vlmclip_encoder_fwd")
+                                                 N.ptr(stats), N.ptr(part), N.ptr(self._row_counters(layers, M, dev)),
+                                                 N.ptr(key_mask), B, S, H, D, F, float(eps), 1 if causal else 0,
+                                                 N.ACT_QUICK_GELU, N.stream()), "vlmclip_encoder_fwd")
             if cls_only:
                 return Hidden(self._last_layer_cls(x, L=layers[-1], B=B, S=S, H=H, eps=eps, qkv=qkv, stats=stats, part=part,
                                                    first=n_full == 0))

@@ -244,6 +244,9 @@ class CLIPAdapterTrainer:
         main.synchronize()
         n0 = N.launch_count()
         g_t = torch.cuda.CUDAGraph()
+        dump = os.environ.get("VLMCLIP_GRAPH_DUMP")  # development aid: DOT files of the two graphs (edge types, node count)
+        if dump:
+            g_t.enable_debug_mode()
         with torch.cuda.graph(g_t):
             with torch.no_grad():
                 st["pooled_T"] = m.tower_pooled(st["inputs"]["input_ids"], st["inputs"]["attention_mask"],
@@ -251,6 +254,9 @@ class CLIPAdapterTrainer:
         n1 = N.launch_count()
         st["pooled_H"] = tuple(torch.zeros_like(t) for t in st["pooled_T"])
         g_h = torch.cuda.CUDAGraph()
+        if dump:
+            g_t.debug_dump(dump + ".towers.dot")
+            g_h.enable_debug_mode()
         with torch.cuda.graph(g_h):
             loss = m.loss_from_pooled(*st["pooled_H"])["loss"]
             opt = self.optimizer
@@ -261,6 +267,8 @@ class CLIPAdapterTrainer:
             st["loss"] = loss.detach()
         self.graph_launches_per_step = int(N.launch_count() - n0)
         self.graph_launches_towers = int(n1 - n0)
+        if dump:
+            g_h.debug_dump(dump + ".heads.dot")
         # capture only records: the effects of a step (optimizer update, Adam step counter) happen on replay
         st["copied"].record(main)
         st["G_T"], st["G_H"] = g_t, g_h
