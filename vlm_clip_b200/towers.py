@@ -87,7 +87,11 @@ def _pack_layers(sd: Dict[str, torch.Tensor], prefix: str, dev, keep_raw: bool) 
 
 
 _STATS_IN_GEMM = os.environ.get("VLMCLIP_STATS_IN_GEMM", "0") == "1"  # experiment switch
-_FUSED_STATS = os.environ.get("VLMCLIP_FUSED_STATS", "1") != "0"      # residual GEMMs finalise the LN statistics
+# Residual GEMMs finalise the LN statistics themselves (last-arriving CTA of a row block) instead of a separate
+# ln_partials_to_stats launch.  OFF: interleaved A/B on B200 (tools/ab_step.py fused_stats, profiles/r02_ab_interleaved.txt)
+# measured 13.31 ms per step fused against 12.94 ms with the 46 separate launches - the two extra barriers that join
+# both epilogue groups at the end of every tile cost more than the launch-bound statistics kernels they replace.
+_FUSED_STATS = os.environ.get("VLMCLIP_FUSED_STATS", "0") == "1"
 
 
 class Hidden:
@@ -186,7 +190,7 @@ class NativeClipTowers:
     def _row_counters(self, layers, M: int, dev):
         """Zeroed int32 words for the fused LayerNorm statistics of the residual GEMMs (one per 128-row block; every
         launch leaves them zero).  One buffer per tower: the towers run concurrently on two streams.
-        VLMCLIP_FUSED_STATS=0 returns None: separate ln_partials_to_stats launches (A/B switch)."""
+        Returns None (separate ln_partials_to_stats launches) unless VLMCLIP_FUSED_STATS=1: see _FUSED_STATS."""
         if not _FUSED_STATS:
             return None
         key = ("cnt", id(layers))
