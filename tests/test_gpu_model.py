@@ -574,6 +574,66 @@ def test_cuda_graph_step_matches_eager_step(cuda, clip_b32, tmp_path):
     assert torch.equal(out_g["loss"], out_e["loss"])
 
 
+def test_reference_trainer_loop_drives_the_mirror_model(cuda, clip_b32, tmp_path):
+    """The drop-in claim at the trainer boundary: the reference's OWN, unmodified
+    `trainer.CLIPAdapterTrainer.train` loop (trainer.py:50-125: name filter, torch.optim.AdamW, linear warm-up schedule,
+    clip_grad_norm_, loss.item()) runs over the mirror `CLIPWithAdapters` bound under the reference's module name, as
+    INTEGRATION.md describes, and takes the same trajectory as the mirror trainer (fused clip + AdamW) on the same
+    batches.  Needs the reference's files staged by oracle/stage_reference.py (they travel with the snapshot)."""
+    import importlib
+    import sys
+
+    from oracle import ref_harness as H
+
+    if not H.available():
+        pytest.skip("oracle/_ref/reference is not staged (run oracle/stage_reference.py where /root/reference exists)")
+    import vlm_clip_b200.model_m as mirror_model_m
+    from vlm_clip_b200.trainer import CLIPAdapterTrainer as MirrorTrainer
+
+    saved = {k: sys.modules.get(k) for k in ("model_m", "trainer")}
+    sys.modules["model_m"] = mirror_model_m            # the binding INTEGRATION.md prescribes
+    sys.modules.pop("trainer", None)
+    sys.path.insert(0, str(H.STAGED))
+    try:
+        ref_trainer = importlib.import_module("trainer")  # the reference's trainer.py, byte for byte
+        assert ref_trainer.CLIPWithAdapters is mirror_model_m.CLIPWithAdapters
+
+        def batches():
+            out = []
+            for s_ in range(4):
+                pix, ids, mask = O.synthetic_batch(4, seed=60 + s_)
+                ids[:, 0] = torch.arange(4) * 9 + s_
+                out.append({"input_ids": ids, "attention_mask": mask, "pixel_values": pix})
+            return out
+
+        m_ref = _make_model(cuda, clip_b32, seed=11)
+        tr_ref = ref_trainer.CLIPAdapterTrainer(m_ref, batches(), learning_rate=1e-3, warmup_steps=2,
+                                                output_dir=str(tmp_path / "ref"))
+        assert len(tr_ref.trainable_params) == 12 and isinstance(tr_ref.optimizer, torch.optim.AdamW)
+        tr_ref.train(num_epochs=2)                      # 8 steps through the reference's loop
+        m_mir = _make_model(cuda, clip_b32, seed=11)
+        tr_mir = MirrorTrainer(m_mir, batches(), learning_rate=1e-3, warmup_steps=2, output_dir=str(tmp_path / "mir"),
+                               log_every=1000)
+        tr_mir.train(num_epochs=2)
+    finally:
+        sys.path.remove(str(H.STAGED))
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for (n1, p1), (n2, p2) in zip(m_ref.named_parameters(), m_mir.named_parameters()):
+        if "adapter" not in n1:
+            continue
+        assert n1 == n2
+        step = (p1 - p2).abs().max().item()
+        # 8 Adam steps of ~1e-3 each: the two optimisers (torch's foreach AdamW vs the fused kernel) agree to fp32 rounding
+        assert step < 2e-5, (n1, step)
+    assert (tmp_path / "ref" / "final_adapter.pt").exists()  # the reference's save path works on the mirror's checkpoint API
+    blob = torch.load(tmp_path / "ref" / "final_adapter.pt")
+    assert set(blob) == {"text_adapter", "vision_adapter"}
+
+
 def test_resume_continues_like_an_uninterrupted_run(cuda, clip_b32, tmp_path):
     """SURVEY.md 8f-4 (the reference has no resume, trainer.py:157-167): 6 steps in one go == 3 steps, save, fresh
     trainer + model, load, 3 more steps.  Compares parameters, both Adam moments, the step counter and the position in

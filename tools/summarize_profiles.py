@@ -21,8 +21,11 @@ def launch_summary():
     for n, v in rows:
         a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
     tot = sum(a[1] for a in agg.values())
-    out = [f"# {tag} ncu launch list: `VLMCLIP_OVERLAP_TOWERS=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`,",
-           "# ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 520 (about 2.5 steps; cold-cache and",
+    cmd = ("VLMCLIP_OVERLAP_TOWERS=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-finetune --no-graph --lean "
+           "--settle-s 0" if tag != "r01" else "VLMCLIP_OVERLAP_TOWERS=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline")
+    skip = 1200 if tag != "r01" else 700
+    out = [f"# {tag} ncu launch list: `{cmd}`,",
+           f"# ncu --metrics gpu__time_duration.sum --clock-control none -s {skip} -c 520 (about 2.3 steps; cold-cache and",
            f"# serialised: compare SHARES, not absolutes).  raw CSV: {tag}_launches_bench.csv", f"total {tot:.0f} us over {len(rows)} launches", ""]
     for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"{a[1]:10.1f} us {100*a[1]/tot:5.1f}% n={a[0]:4d} avg={a[1]/a[0]:8.1f}  {n}")
@@ -80,4 +83,8 @@ if __name__ == "__main__":
                "launches": ["qkv", "out_proj", "fc1", "fc2"], "dram_bytes": per,
                "dram_bytes_per_launch": sum(per) / len(per)}, open(OUT / "gemm_traffic.json", "w"), indent=1)
     report("prof_attn.ncu-rep", f"{tag}_attention_pp.txt", "tcgen05 ping-pong attention, vision (B=256, S=197, H=12)", ["vision"])
+    if (G / "prof_loss.ncu-rep").exists():
+        report("prof_loss.ncu-rep", f"{tag}_clip_loss_strips.txt",
+               "strip-wise contrastive loss at N = 4096, P = 768, 512 local rows (tools/loss_only.py)",
+               ["norm2", "strip_lse", "strip_grad"])
     print("ok")

@@ -15,13 +15,13 @@
 //
 // Three launches (the previous path: eight, on the full N x N matrix on every rank):
 //   clip_norm2_kernel        both feature matrices -> unit rows + 1/norm
-//   clip_strip_lse_kernel    64 x 64 fp32 register tiles over (row block, column split, problem); running (max, sum) of
-//                            every row in registers, merged across the 16 threads of a row with warp shuffles; the
-//                            last-arriving CTA of a row block merges the column splits in fixed order and the very last
-//                            CTA adds up the loss: deterministic, no floating-point atomics
-//   clip_strip_grad_kernel   dA = G B with G formed on the fly from the stored strip; the last-arriving CTA of a row
-//                            block (over the column tiles of P) applies the normalisation backward, which needs the
-//                            full-row dot product
+//   clip_strip_lse_kernel    128 x 128 fp32 register tiles (8 x 8 outputs per thread) over (row block, column split,
+//                            problem); running (max, sum) of every row in registers, merged across the 16 threads of a
+//                            row with warp shuffles; the last-arriving CTA of a row block merges the column splits in
+//                            fixed order and the very last CTA adds up the loss: deterministic, no floating-point atomics
+//   clip_strip_grad_kernel   dA = G B with G formed on the fly from the stored strip, the reduction over the N columns
+//                            split across CTAs; the last-arriving CTA of a row block adds the splits in index order and
+//                            applies the normalisation backward, which needs the full-row dot product
 // fp32 SIMT on purpose: the loss must match the reference's fp32 value to 1e-4 at a logit scale of 100, i.e. cosines
 // to ~1e-7; the whole path is ~13 GFLOP at N = 4096 (0.02 % of that step).
 #include "../../include/vlmclip.h"
@@ -32,9 +32,9 @@ void count_launch(int n);
 
 namespace {
 
-constexpr int CL_TILE = 64;
-constexpr int CL_KC = 16;
-constexpr int CL_THREADS = 256;  // 16 x 16 threads, 4 x 4 outputs each
+constexpr int CL_TILE = 128;     // CTA tile: 128 x 128 outputs
+constexpr int CL_KC = 16;        // reduction chunk staged through shared memory
+constexpr int CL_THREADS = 256;  // 16 x 16 threads, 8 x 8 outputs each (two 4-row groups x two 4-column groups, 64 apart)
 constexpr int CL_PAD = 4;
 
 __global__ void __launch_bounds__(256)
@@ -53,41 +53,58 @@ clip_norm2_kernel(const float* __restrict__ txt, const float* __restrict__ img, 
   if (lane == 0) (is_img ? inv_i : inv_t)[row] = inv;
 }
 
-// acc[i][j] += sum_k A(ty*4+i, k) * B(tx*4+j, k) over k in [0, K), in chunks of 16 through shared memory; the next
-// chunk is fetched into registers while the current one is multiplied.  fetchA / fetchB(k0, regs[4]) return the four
-// elements this thread stages for chunk k0, storeA / storeB(regs) put them into As / Bs (layout [k][m]).
+// 128 x 128 x K fp32 tile product.  Thread (tx, ty) = (tid & 15, tid >> 4) owns rows {ty*4 + i, 64 + ty*4 + i} and
+// columns {tx*4 + j, 64 + tx*4 + j}, i, j < 4 (acc[8][8]): per k four 16-byte shared loads feed 64 FMAs, and the 16
+// threads of a half-warp share their rows, so row reductions are shuffles.  K runs in chunks of 16 through shared memory
+// (layout [k][m]); the next chunk is fetched into registers while the current one is multiplied.
+// fetchA / fetchB(k0, regs[8]) return the eight elements this thread stages for chunk k0, storeA / storeB put them away.
 struct TileSmem {
   float As[CL_KC][CL_TILE + CL_PAD];
   float Bs[CL_KC][CL_TILE + CL_PAD];
 };
 
+__device__ __forceinline__ int tile_row(int ty, int i) { return (i < 4 ? 0 : 60) + ty * 4 + i; }  // i >= 4: 64 + ty*4 + i - 4
+__device__ __forceinline__ int tile_col(int tx, int j) { return (j < 4 ? 0 : 60) + tx * 4 + j; }
+
 template <class FetchA, class FetchB, class StoreA, class StoreB>
-__device__ __forceinline__ void tile64_mainloop(TileSmem& sm, int K, float (&acc)[4][4], FetchA fetchA, FetchB fetchB,
-                                                StoreA storeA, StoreB storeB) {
+__device__ __forceinline__ void tile128_mainloop(TileSmem& sm, int k_begin, int k_end, float (&acc)[8][8], FetchA fetchA,
+                                                 FetchB fetchB, StoreA storeA, StoreB storeB) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float ra[4], rb[4];
-  fetchA(0, ra);
-  fetchB(0, rb);
-  for (int k0 = 0; k0 < K; k0 += CL_KC) {
+  float ra[8], rb[8];
+  fetchA(k_begin, ra);
+  fetchB(k_begin, rb);
+  for (int k0 = k_begin; k0 < k_end; k0 += CL_KC) {
     storeA(ra);
     storeB(rb);
     __syncthreads();
-    if (k0 + CL_KC < K) {
+    if (k0 + CL_KC < k_end) {
       fetchA(k0 + CL_KC, ra);
       fetchB(k0 + CL_KC, rb);
     }
 #pragma unroll
     for (int kk = 0; kk < CL_KC; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&sm.As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&sm.Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&sm.As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sm.As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sm.Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sm.Bs[kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+  }
+}
+
+// staging of a k-contiguous operand (row-major [rows, K]): thread t takes a float4 along k of rows t/4 and 64 + t/4
+__device__ __forceinline__ void stage_kfast(float (*S)[CL_TILE + CL_PAD], const float (&r)[8]) {
+  const int lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    S[lk + j][lrow] = r[j];
+    S[lk + j][64 + lrow] = r[4 + j];
   }
 }
 
@@ -106,7 +123,7 @@ struct StripParams {
   int N, P, row0, nloc, ldz, nsplit, cols_per_split;
 };
 
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 2)
 clip_strip_lse_kernel(const StripParams p) {
   __shared__ TileSmem sm;
   __shared__ unsigned s_last;
@@ -116,55 +133,48 @@ clip_strip_lse_kernel(const StripParams p) {
   const int a0 = rb * CL_TILE;
   const float* A = (prob == 0 ? p.txt_n : p.img_n) + (int64_t)p.row0 * p.P;  // local rows
   const float* B = prob == 0 ? p.img_n : p.txt_n;                           // every row
-  float* Z = p.z[prob];
+  float* Z = prob == 0 ? p.z[0] : p.z[1];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // staging: one float4 along k of row lrow
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // staging: float4 along k of rows lrow and 64 + lrow
   const int c_begin = split * p.cols_per_split;
   const int c_end = min(p.N, c_begin + p.cols_per_split);
 
-  float run_m[4], run_l[4];
+  float run_m[8], run_l[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     run_m[i] = -INFINITY;
     run_l[i] = 0.f;
   }
   for (int b0 = c_begin; b0 < c_end; b0 += CL_TILE) {
-    float acc[4][4];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const bool a_ok = a0 + lrow < p.nloc;
-    const bool b_ok = b0 + lrow < c_end;
-    const float* ap = A + (int64_t)(a0 + lrow) * p.P + lk;
-    const float* bp = B + (int64_t)(b0 + lrow) * p.P + lk;
-    auto fetch = [&](const float* src, bool ok, int k0, float (&r)[4]) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && k0 + lk < p.P) v = __ldg(reinterpret_cast<const float4*>(src + k0));
-      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    auto fetch = [&](const float* base, int r0, int rlim, int k0, float (&r)[8]) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = r0 + lrow + 64 * h;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rlim && k0 + lk < p.P) v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)row * p.P + k0 + lk));
+        r[4 * h + 0] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+      }
     };
-    tile64_mainloop(
-        sm, p.P, acc, [&](int k0, float (&r)[4]) { fetch(ap, a_ok, k0, r); },
-        [&](int k0, float (&r)[4]) { fetch(bp, b_ok, k0, r); },
-        [&](const float (&r)[4]) {
+    tile128_mainloop(
+        sm, 0, p.P, acc, [&](int k0, float (&r)[8]) { fetch(A, a0, p.nloc, k0, r); },
+        [&](int k0, float (&r)[8]) { fetch(B, b0, c_end, k0, r); }, [&](const float (&r)[8]) { stage_kfast(sm.As, r); },
+        [&](const float (&r)[8]) { stage_kfast(sm.Bs, r); });
+    // epilogue of the tile: scale, store the strip, diagonal, running log-sum-exp of the thread's eight rows
 #pragma unroll
-          for (int j = 0; j < 4; ++j) sm.As[lk + j][lrow] = r[j];
-        },
-        [&](const float (&r)[4]) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sm.Bs[lk + j][lrow] = r[j];
-        });
-    // epilogue of the tile: scale, store the strip, diagonal, running log-sum-exp of the thread's four rows
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int a = a0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+      const int a = a0 + tile_row(ty, i);
       if (a >= p.nloc) continue;
-      float z[4];
+      float z[8];
       float tm = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int b = b0 + tx * 4 + j;
+      for (int j = 0; j < 8; ++j) {
+        const int b = b0 + tile_col(tx, j);
         z[j] = p.s * acc[i][j];
         if (b < c_end) {
           Z[(int64_t)a * p.ldz + b] = z[j];
@@ -181,13 +191,13 @@ clip_strip_lse_kernel(const StripParams p) {
       }
       if (run_m[i] > -INFINITY) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) run_l[i] += __expf(z[j] - run_m[i]);
+        for (int j = 0; j < 8; ++j) run_l[i] += __expf(z[j] - run_m[i]);
       }
     }
   }
   // merge the 16 threads that share a row (the tx dimension = one half-warp): (max, sum) pairs through shuffles
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     float m = run_m[i], l = run_l[i];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
@@ -197,7 +207,7 @@ clip_strip_lse_kernel(const StripParams p) {
       l = (m > -INFINITY ? l * __expf(m - mm) : 0.f) + (m2 > -INFINITY ? l2 * __expf(m2 - mm) : 0.f);
       m = mm;
     }
-    const int a = a0 + ty * 4 + i;
+    const int a = a0 + tile_row(ty, i);
     if (tx == 0 && a < p.nloc) p.part[((int64_t)prob * p.nsplit + split) * p.nloc + a] = make_float2(m, l);
   }
   // ---- last-arriving CTA of this (problem, row block): merge the column splits in index order ----
@@ -208,7 +218,7 @@ clip_strip_lse_kernel(const StripParams p) {
   __syncthreads();
   if (s_last == 0u) return;
   __threadfence();
-  float* red = &sm.As[0][0];  // 64 floats of scratch
+  float* red = &sm.As[0][0];  // 128 floats of scratch
   if (tid < CL_TILE) {
     const int a = a0 + tid;
     float term = 0.f;
@@ -222,7 +232,7 @@ clip_strip_lse_kernel(const StripParams p) {
         m = mm;
       }
       const float lse = m + logf(l);
-      p.lse[prob][a] = lse;
+      (prob == 0 ? p.lse[0] : p.lse[1])[a] = lse;
       term = lse - __ldcg(&p.diag[prob * p.nloc + a]);
     }
     red[tid] = term;
@@ -256,11 +266,12 @@ struct GradParams {
   // image-side one rows_per_rank further
   const float* lse_all;
   int lse_stride, rows_per_rank;
-  float* dn[2];           // [nloc, P] gradients w.r.t. the unit rows (scratch)
+  float* dn;              // [ksplit][2][nloc, P] partial gradients w.r.t. the unit rows (one plane per reduction split)
   float* d[2];            // [nloc, P] outputs: d_txt, d_img
   unsigned* counters;     // [2 * row blocks], zero on entry and on exit
   float s;
   int N, P, row0, nloc, ldz, z_row_off;
+  int ptiles, ksplit, k_per_split;  // gridDim.y = ptiles * ksplit
 };
 
 __device__ __forceinline__ float lse_of(const GradParams& p, int side, int r) {
@@ -268,68 +279,90 @@ __device__ __forceinline__ float lse_of(const GradParams& p, int side, int r) {
   return __ldg(p.lse_all + (int64_t)w * p.lse_stride + side * p.rows_per_rank + (r - w * p.rows_per_rank));
 }
 
-__global__ void __launch_bounds__(CL_THREADS)
+__global__ void __launch_bounds__(CL_THREADS, 2)
 clip_strip_grad_kernel(const GradParams p) {
   __shared__ TileSmem sm;
   __shared__ unsigned s_last;
   const int prob = blockIdx.z;
   const int rb = blockIdx.x;
   const int a0 = rb * CL_TILE;
-  const int c0 = blockIdx.y * CL_TILE;  // columns of P
-  const float* Z = p.z[prob] + (int64_t)p.z_row_off * p.ldz;
+  const int ptile = blockIdx.y % p.ptiles, ks = blockIdx.y / p.ptiles;
+  const int c0 = ptile * CL_TILE;  // columns of P
+  const int k_begin = ks * p.k_per_split, k_end = min(p.N, k_begin + p.k_per_split);  // this CTA's share of the reduction
+  const float* Z = (prob == 0 ? p.z[0] : p.z[1]) + (int64_t)p.z_row_off * p.ldz;
   const int sideA = prob, sideB = 1 - prob;  // problem 0: own text-side LSE, the images' LSE for the columns; 1: swapped
   const float* B = prob == 0 ? p.img_n : p.txt_n;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lrow = tid >> 2, lk = (tid & 3) * 4;   // A staging: float4 along b (the reduction index) of row lrow
-  const int bk = tid >> 4, bn = (tid & 15) * 4;    // B staging: float4 along the P columns of reduction row bk
-  float acc[4][4];
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // A staging: float4 along b (the reduction index) of rows lrow, 64 + lrow
+  const int bk = tid >> 5, bn = (tid & 31) * 4;   // B staging: float4 along the P columns of reduction rows bk, 8 + bk
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const bool a_ok = a0 + lrow < p.nloc;
-  const float my_lse = a_ok ? lse_of(p, sideA, p.row0 + a0 + lrow) : 0.f;
-  const int my_diag = p.row0 + a0 + lrow;
-  const float* zp = Z + (int64_t)(a0 + lrow) * p.ldz + lk;
-  tile64_mainloop(
-      sm, p.N, acc,
-      [&](int k0, float (&r)[4]) {  // G[a, b] for b = k0 + lk .. + 3
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float my_lse[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    a_ok[h] = a0 + lrow + 64 * h < p.nloc;
+    my_lse[h] = a_ok[h] ? lse_of(p, sideA, p.row0 + a0 + lrow + 64 * h) : 0.f;
+  }
+  tile128_mainloop(
+      sm, k_begin, k_end, acc,
+      [&](int k0, float (&r)[8]) {  // G[a, b] for b = k0 + lk .. + 3, rows lrow and 64 + lrow
         const int b = k0 + lk;
-        if (a_ok && b < p.N) v = __ldg(reinterpret_cast<const float4*>(zp + k0));  // ldz is a multiple of 4
-        const float zz[4] = {v.x, v.y, v.z, v.w};
+        float lb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float g = 0.f;
-          if (a_ok && b + j < p.N) {
-            g = __expf(zz[j] - my_lse) + __expf(zz[j] - lse_of(p, sideB, b + j));
-            if (b + j == my_diag) g -= 2.f;
+        for (int j = 0; j < 4; ++j) lb[j] = b + j < k_end ? lse_of(p, sideB, b + j) : 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int a = a0 + lrow + 64 * h;
+          if (a_ok[h] && b < k_end) v = __ldg(reinterpret_cast<const float4*>(Z + (int64_t)a * p.ldz + b));  // ldz % 4 == 0
+          const float zz[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float g = 0.f;
+            if (a_ok[h] && b + j < k_end) {
+              g = __expf(zz[j] - my_lse[h]) + __expf(zz[j] - lb[j]);
+              if (b + j == p.row0 + a) g -= 2.f;
+            }
+            r[4 * h + j] = g;
           }
-          r[j] = g;
         }
       },
-      [&](int k0, float (&r)[4]) {  // B[b, c0 + bn .. + 3] for b = k0 + bk
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + bk < p.N && c0 + bn < p.P) v = __ldg(reinterpret_cast<const float4*>(B + (int64_t)(k0 + bk) * p.P + c0 + bn));
-        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-      },
-      [&](const float (&r)[4]) {
+      [&](int k0, float (&r)[8]) {  // B[b, c0 + bn .. + 3] for b = k0 + bk and k0 + 8 + bk
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sm.As[lk + j][lrow] = r[j];
+        for (int h = 0; h < 2; ++h) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int b = k0 + bk + 8 * h;
+          if (b < k_end && c0 + bn < p.P) v = __ldg(reinterpret_cast<const float4*>(B + (int64_t)b * p.P + c0 + bn));
+          r[4 * h + 0] = v.x; r[4 * h + 1] = v.y; r[4 * h + 2] = v.z; r[4 * h + 3] = v.w;
+        }
       },
-      [&](const float (&r)[4]) { *reinterpret_cast<float4*>(&sm.Bs[bk][bn]) = make_float4(r[0], r[1], r[2], r[3]); });
+      [&](const float (&r)[8]) { stage_kfast(sm.As, r); },
+      [&](const float (&r)[8]) {
+        *reinterpret_cast<float4*>(&sm.Bs[bk][bn]) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(&sm.Bs[8 + bk][bn]) = make_float4(r[4], r[5], r[6], r[7]);
+      });
   const float coef = p.s / (2.f * (float)p.N);
-  float* dn = p.dn[prob];
+  const int64_t plane = (int64_t)p.nloc * p.P;
+  float* dn = p.dn + ((int64_t)ks * 2 + prob) * plane;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int a = a0 + ty * 4 + i;
-    const int c = c0 + tx * 4;
-    if (a < p.nloc && c < p.P)
-      *reinterpret_cast<float4*>(dn + (int64_t)a * p.P + c) =
-          make_float4(coef * acc[i][0], coef * acc[i][1], coef * acc[i][2], coef * acc[i][3]);
+  for (int i = 0; i < 8; ++i) {
+    const int a = a0 + tile_row(ty, i);
+    if (a >= p.nloc) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 64 * h + tx * 4;
+      if (c < p.P)
+        *reinterpret_cast<float4*>(dn + (int64_t)a * p.P + c) = make_float4(
+            coef * acc[i][4 * h + 0], coef * acc[i][4 * h + 1], coef * acc[i][4 * h + 2], coef * acc[i][4 * h + 3]);
+    }
   }
-  // ---- last-arriving CTA of this (problem, row block): back through the normalisation, which needs whole rows ----
+  // ---- last-arriving CTA of this (problem, row block): add the reduction splits in index order, then back through the
+  // normalisation, which needs whole rows ----
   __threadfence();
   __syncthreads();
   const int nrb = gridDim.x;
@@ -339,18 +372,23 @@ clip_strip_grad_kernel(const GradParams p) {
   __threadfence();
   const float* An = (prob == 0 ? p.txt_n : p.img_n) + (int64_t)p.row0 * p.P;
   const float* inv = (prob == 0 ? p.inv_t : p.inv_i) + p.row0;
-  float* out = p.d[prob];
+  float* out = prob == 0 ? p.d[0] : p.d[1];
+  float* sum0 = p.dn + (int64_t)prob * plane;  // split 0's plane receives the sum over the splits
   const int warp = tid >> 5, lane = tid & 31;
   for (int r = warp; r < CL_TILE; r += CL_THREADS / 32) {
     const int a = a0 + r;
     if (a >= p.nloc) break;
     const float* xn = An + (int64_t)a * p.P;
-    const float* dr = dn + (int64_t)a * p.P;
     float dot = 0.f;
-    for (int c = lane; c < p.P; c += 32) dot = fmaf(xn[c], __ldcg(dr + c), dot);
+    for (int c = lane; c < p.P; c += 32) {
+      float v = 0.f;
+      for (int k = 0; k < p.ksplit; ++k) v += __ldcg(p.dn + ((int64_t)k * 2 + prob) * plane + (int64_t)a * p.P + c);
+      sum0[(int64_t)a * p.P + c] = v;  // read back below by the same thread
+      dot = fmaf(xn[c], v, dot);
+    }
     dot = warp_sum(dot);
     const float iv = inv[a];
-    for (int c = lane; c < p.P; c += 32) out[(int64_t)a * p.P + c] = (__ldcg(dr + c) - xn[c] * dot) * iv;
+    for (int c = lane; c < p.P; c += 32) out[(int64_t)a * p.P + c] = (sum0[(int64_t)a * p.P + c] - xn[c] * dot) * iv;
   }
   if (tid == 0) p.counters[prob * nrb + rb] = 0u;
 }
@@ -391,13 +429,30 @@ scale_f32_kernel(const float* __restrict__ a, const float* __restrict__ sc, floa
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
-// column splits of the strip kernel: enough CTAs to fill the GPU, at least one 64-column tile each
+// column splits of the strip kernel: enough CTAs for two per SM, at least one 128-column tile each
 inline int pick_nsplit(int N, int nloc) {
   const int rbs = ceil_div(nloc, CL_TILE) * 2;
   int want = ceil_div(2 * sm_count(), rbs);
   const int max_split = ceil_div(N, CL_TILE);
   if (want > max_split) want = max_split;
   return want < 1 ? 1 : want;
+}
+
+// reduction splits of the gradient kernel (its output tiles alone are few: nloc/128 x P/128 x 2)
+struct GradSplit {
+  int ptiles, ksplit, k_per_split;
+};
+inline GradSplit grad_split(int N, int P, int nloc) {
+  GradSplit g;
+  g.ptiles = ceil_div(P, CL_TILE);
+  const int base = ceil_div(nloc, CL_TILE) * g.ptiles * 2;
+  int want = ceil_div(2 * sm_count(), base);
+  const int max_split = ceil_div(N, 2 * CL_TILE);  // at least 256 reduction rows per split
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  g.k_per_split = ceil_div(ceil_div(N, want), CL_KC) * CL_KC;
+  g.ksplit = ceil_div(N, g.k_per_split);
+  return g;
 }
 
 struct FwdLayout {
@@ -435,8 +490,7 @@ using namespace vlmclip;
 extern "C" int64_t vlmclip_clip_loss_state_size(int N, int P, int nloc) { return fwd_layout(N, P, nloc).total; }
 extern "C" int64_t vlmclip_clip_loss_counters(int nloc) { return 4 * (int64_t)ceil_div(nloc, CL_TILE) + 4; }
 extern "C" int64_t vlmclip_clip_loss_bwd_workspace(int N, int P, int nloc) {
-  (void)N;
-  return 2 * (int64_t)nloc * P;
+  return (int64_t)grad_split(N, P, nloc).ksplit * 2 * (int64_t)nloc * P;
 }
 
 // Forward on the strips of rows [row0, row0 + nloc).  txt / img: the (all-gathered) un-normalised features [N, P];
@@ -513,8 +567,11 @@ extern "C" int vlmclip_clip_loss_bwd(const float* txt_n, const float* img_n, con
   g.lse_all = lse_all;
   g.lse_stride = lse_stride;
   g.rows_per_rank = rows_per_rank;
-  g.dn[0] = workspace;
-  g.dn[1] = workspace + (int64_t)nloc * P;
+  const GradSplit gs = grad_split(N, P, nloc);
+  g.dn = workspace;
+  g.ptiles = gs.ptiles;
+  g.ksplit = gs.ksplit;
+  g.k_per_split = gs.k_per_split;
   g.d[0] = d_txt;
   g.d[1] = d_img;
   const int nrb = ceil_div(nloc, CL_TILE);
@@ -527,7 +584,7 @@ extern "C" int vlmclip_clip_loss_bwd(const float* txt_n, const float* img_n, con
   g.ldz = L.ldz;
   g.z_row_off = row0 - strip_row0;
   count_launch(1);
-  clip_strip_grad_kernel<<<dim3(nrb, ceil_div(P, CL_TILE), 2), CL_THREADS, 0, s>>>(g);
+  clip_strip_grad_kernel<<<dim3(nrb, gs.ptiles * gs.ksplit, 2), CL_THREADS, 0, s>>>(g);
   if (d_logit_scale != nullptr) {
     // the local LSEs: block of this rank (exchange layout) or rows [row0, ..) of the single block
     const int w = row0 / rows_per_rank, r = row0 - w * rows_per_rank;
