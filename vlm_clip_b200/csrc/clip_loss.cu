@@ -267,8 +267,9 @@ struct GradParams {
   const float* lse_all;
   int lse_stride, rows_per_rank;
   float* dn;              // [ksplit][2][nloc, P] partial gradients w.r.t. the unit rows (one plane per reduction split)
+  float* dotp;            // [2][nloc][ptiles] per-P-tile partial dot products (unit row . summed gradient)
   float* d[2];            // [nloc, P] outputs: d_txt, d_img
-  unsigned* counters;     // [2 * row blocks], zero on entry and on exit
+  unsigned* counters;     // [2 * row blocks] level 2, then [2 * row blocks * ptiles] level 1; zero on entry and on exit
   float s;
   int N, P, row0, nloc, ldz, z_row_off;
   int ptiles, ksplit, k_per_split;  // gridDim.y = ptiles * ksplit
@@ -313,8 +314,18 @@ clip_strip_grad_kernel(const GradParams p) {
       [&](int k0, float (&r)[8]) {  // G[a, b] for b = k0 + lk .. + 3, rows lrow and 64 + lrow
         const int b = k0 + lk;
         float lb[4];
+        {
+          // one division for the four consecutive columns (they share a rank block unless they straddle its end)
+          const int w = b / p.rows_per_rank, off = b - w * p.rows_per_rank;
+          const float* lp = p.lse_all + (int64_t)w * p.lse_stride + sideB * p.rows_per_rank + off;
+          if (off + 3 < p.rows_per_rank && b + 3 < k_end) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) lb[j] = b + j < k_end ? lse_of(p, sideB, b + j) : 0.f;
+            for (int j = 0; j < 4; ++j) lb[j] = __ldg(lp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lb[j] = b + j < k_end ? lse_of(p, sideB, b + j) : 0.f;
+          }
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -361,36 +372,69 @@ clip_strip_grad_kernel(const GradParams p) {
             coef * acc[i][4 * h + 0], coef * acc[i][4 * h + 1], coef * acc[i][4 * h + 2], coef * acc[i][4 * h + 3]);
     }
   }
-  // ---- last-arriving CTA of this (problem, row block): add the reduction splits in index order, then back through the
-  // normalisation, which needs whole rows ----
+  // ---- two-level last-arriver reduction (fixed summation orders: deterministic) ----
+  // level 1, per (problem, row block, P tile): the CTA that completes the tile's last reduction split adds the splits in
+  // index order into split 0's plane and leaves each row's partial dot product with its unit row;
+  // level 2, per (problem, row block): the CTA that completes the block's last P tile goes back through the
+  // normalisation, which needs the whole-row dot product.
   __threadfence();
   __syncthreads();
   const int nrb = gridDim.x;
-  if (tid == 0) s_last = atomicAdd(&p.counters[prob * nrb + rb], 1u) == gridDim.y - 1 ? 1u : 0u;
+  unsigned* cnt1 = p.counters + 2 * nrb + ((prob * nrb + rb) * p.ptiles + ptile);
+  unsigned* cnt2 = p.counters + prob * nrb + rb;
+  if (tid == 0) s_last = atomicAdd(cnt1, 1u) == (unsigned)(p.ksplit - 1) ? 1u : 0u;
   __syncthreads();
   if (s_last == 0u) return;
   __threadfence();
   const float* An = (prob == 0 ? p.txt_n : p.img_n) + (int64_t)p.row0 * p.P;
   const float* inv = (prob == 0 ? p.inv_t : p.inv_i) + p.row0;
   float* out = prob == 0 ? p.d[0] : p.d[1];
-  float* sum0 = p.dn + (int64_t)prob * plane;  // split 0's plane receives the sum over the splits
+  float* sum0 = p.dn + (int64_t)prob * plane;  // split 0's plane of this problem
+  float* dotp = p.dotp + (int64_t)prob * p.nloc * p.ptiles;
   const int warp = tid >> 5, lane = tid & 31;
+  {
+    const int c = c0 + lane * 4;  // 32 lanes x 4 columns = the tile's 128 columns
+    for (int r = warp; r < CL_TILE; r += CL_THREADS / 32) {
+      const int a = a0 + r;
+      if (a >= p.nloc) break;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float pd = 0.f;
+      if (c < p.P) {
+        for (int k = 0; k < p.ksplit; ++k) {
+          const float4 q = __ldcg(reinterpret_cast<const float4*>(p.dn + ((int64_t)k * 2 + prob) * plane + (int64_t)a * p.P + c));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        *reinterpret_cast<float4*>(sum0 + (int64_t)a * p.P + c) = v;
+        const float4 x = *reinterpret_cast<const float4*>(An + (int64_t)a * p.P + c);
+        pd = x.x * v.x + x.y * v.y + x.z * v.z + x.w * v.w;
+      }
+      pd = warp_sum(pd);
+      if (lane == 0) dotp[(int64_t)a * p.ptiles + ptile] = pd;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    *cnt1 = 0u;
+    s_last = atomicAdd(cnt2, 1u) == (unsigned)(p.ptiles - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
   for (int r = warp; r < CL_TILE; r += CL_THREADS / 32) {
     const int a = a0 + r;
     if (a >= p.nloc) break;
-    const float* xn = An + (int64_t)a * p.P;
     float dot = 0.f;
-    for (int c = lane; c < p.P; c += 32) {
-      float v = 0.f;
-      for (int k = 0; k < p.ksplit; ++k) v += __ldcg(p.dn + ((int64_t)k * 2 + prob) * plane + (int64_t)a * p.P + c);
-      sum0[(int64_t)a * p.P + c] = v;  // read back below by the same thread
-      dot = fmaf(xn[c], v, dot);
-    }
-    dot = warp_sum(dot);
+    for (int t = 0; t < p.ptiles; ++t) dot += __ldcg(dotp + (int64_t)a * p.ptiles + t);  // index order
     const float iv = inv[a];
-    for (int c = lane; c < p.P; c += 32) out[(int64_t)a * p.P + c] = (sum0[(int64_t)a * p.P + c] - xn[c] * dot) * iv;
+    for (int c = lane * 4; c < p.P; c += 128) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(sum0 + (int64_t)a * p.P + c));
+      const float4 x = *reinterpret_cast<const float4*>(An + (int64_t)a * p.P + c);
+      *reinterpret_cast<float4*>(out + (int64_t)a * p.P + c) =
+          make_float4((v.x - x.x * dot) * iv, (v.y - x.y * dot) * iv, (v.z - x.z * dot) * iv, (v.w - x.w * dot) * iv);
+    }
   }
-  if (tid == 0) p.counters[prob * nrb + rb] = 0u;
+  if (tid == 0) *cnt2 = 0u;
 }
 
 // dL/d(log scale) of this rank's rows and columns (full fine-tune only): sum over the two strips of (P - delta) Z / 2N
@@ -432,7 +476,7 @@ inline int64_t align4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 // column splits of the strip kernel: enough CTAs for two per SM, at least one 128-column tile each
 inline int pick_nsplit(int N, int nloc) {
   const int rbs = ceil_div(nloc, CL_TILE) * 2;
-  int want = ceil_div(2 * sm_count(), rbs);
+  int want = (2 * sm_count()) / rbs;  // floor: one resident wave
   const int max_split = ceil_div(N, CL_TILE);
   if (want > max_split) want = max_split;
   return want < 1 ? 1 : want;
@@ -446,7 +490,7 @@ inline GradSplit grad_split(int N, int P, int nloc) {
   GradSplit g;
   g.ptiles = ceil_div(P, CL_TILE);
   const int base = ceil_div(nloc, CL_TILE) * g.ptiles * 2;
-  int want = ceil_div(2 * sm_count(), base);
+  int want = (2 * sm_count()) / base;  // floor: all CTAs resident at once (two per SM), no second partial wave
   const int max_split = ceil_div(N, 2 * CL_TILE);  // at least 256 reduction rows per split
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
@@ -488,9 +532,11 @@ using namespace vlmclip;
 // (vlmclip_clip_loss_state_size floats).  `counters`: vlmclip_clip_loss_counters(nloc) 32-bit words that must be ZERO
 // before the first call; every kernel leaves them zero again, so one buffer per stream can be reused for ever.
 extern "C" int64_t vlmclip_clip_loss_state_size(int N, int P, int nloc) { return fwd_layout(N, P, nloc).total; }
-extern "C" int64_t vlmclip_clip_loss_counters(int nloc) { return 4 * (int64_t)ceil_div(nloc, CL_TILE) + 4; }
+// strip kernel: 2 nrb + 1; gradient kernel: 2 nrb (level 2) + 2 nrb * ptiles (level 1, ptiles <= 8)
+extern "C" int64_t vlmclip_clip_loss_counters(int nloc) { return 21 * (int64_t)ceil_div(nloc, CL_TILE) + 4; }
 extern "C" int64_t vlmclip_clip_loss_bwd_workspace(int N, int P, int nloc) {
-  return (int64_t)grad_split(N, P, nloc).ksplit * 2 * (int64_t)nloc * P;
+  const GradSplit g = grad_split(N, P, nloc);
+  return (int64_t)g.ksplit * 2 * (int64_t)nloc * P + align4(2 * (int64_t)nloc * g.ptiles);
 }
 
 // Forward on the strips of rows [row0, row0 + nloc).  txt / img: the (all-gathered) un-normalised features [N, P];
@@ -545,7 +591,8 @@ extern "C" int vlmclip_clip_loss_bwd(const float* txt_n, const float* img_n, con
                                      float* d_logit_scale, float* state, int32_t* counters, float* workspace, int N, int P,
                                      int row0, int nloc, int strip_row0, int strip_rows, void* stream) {
   VLMCLIP_CHECK_ARG(txt_n && img_n && lse_all && d_txt && d_img && state && counters && workspace, "clip_loss_bwd: null pointer");
-  VLMCLIP_CHECK_ARG(N > 0 && P > 0 && P % 4 == 0 && row0 >= 0 && nloc > 0 && row0 + nloc <= N, "clip_loss_bwd: bad dims");
+  VLMCLIP_CHECK_ARG(N > 0 && P > 0 && P % 4 == 0 && P <= 1024 && row0 >= 0 && nloc > 0 && row0 + nloc <= N,
+                    "clip_loss_bwd: bad dims (P must be a multiple of 4, at most 1024)");
   VLMCLIP_CHECK_ARG(strip_row0 <= row0 && row0 + nloc <= strip_row0 + strip_rows && strip_row0 >= 0 && strip_row0 + strip_rows <= N,
                     "clip_loss_bwd: rows [%d,%d) are not inside the stored strips [%d,%d)", row0, row0 + nloc, strip_row0,
                     strip_row0 + strip_rows);
@@ -569,6 +616,7 @@ extern "C" int vlmclip_clip_loss_bwd(const float* txt_n, const float* img_n, con
   g.rows_per_rank = rows_per_rank;
   const GradSplit gs = grad_split(N, P, nloc);
   g.dn = workspace;
+  g.dotp = workspace + (int64_t)gs.ksplit * 2 * (int64_t)nloc * P;
   g.ptiles = gs.ptiles;
   g.ksplit = gs.ksplit;
   g.k_per_split = gs.k_per_split;
