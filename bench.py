@@ -312,6 +312,22 @@ def run_native_arm(args):
     sampler.start()
     ms_total, host_ms, n_launch, loss = timed_resident(K, W)
     clocks = sampler.stop()
+    # the trainable half of the step (G_H: final LN, adapters, projections, all-gather, loss, LSE exchange, backward,
+    # gradient all-reduce, clip + AdamW) timed by itself over a few extra steps: it runs UNDER the next step's towers,
+    # so this is its own duration (incl. waiting for SMs and for the slowest rank's collectives), not exposed time
+    tail = None
+    if use_graph:
+        trainer.tail_events = []
+        for i in range(10):
+            trainer.training_step(resident[i % nrot])
+        torch.cuda.synchronize()
+        tms = sorted(a.elapsed_time(b) for a, b in trainer.tail_events)
+        trainer.tail_events = None
+        if tms:
+            tail = {"what": "duration of the trainable half of a step (graph G_H) on the caller's stream, overlapped with the "
+                            "next step's towers: heads, feature all-gather, loss strips, LSE all-gather, backward, gradient "
+                            "all-reduce, clip + AdamW", "ms_median": statistics.median(tms), "ms_max": tms[-1],
+                    "ms_min": tms[0], "steps": len(tms)}
     ms_step = ms_total / K
     value = world * BATCH * K / (ms_total / 1e3)
     final_loss = float(loss.item())
@@ -456,6 +472,7 @@ def run_native_arm(args):
                 "h2d_gbs_needed_to_hide_copy": h2d / (ms_e2e / K / 1e3) / 1e9, "h2d_gbs_isolated_copy": h2d_gbs,
                 "uint8_frames_variant": u8_variant},
         "gpu_launches": int(n_launch),
+        "tail": tail,
         "shortcut_variant": shortcut,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
                      "frac": achieved / peak_sus if peak_sus else None, "traffic": traffic,
