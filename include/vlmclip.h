@@ -86,6 +86,14 @@ int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
 int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
                            int64_t plane_stride, const float* bias, float* stats_part_out, float* stats_out,
                            int32_t* row_counters, float ln_eps, int M, int N, int K, void* stream);
+/* Split reduction for GEMMs with few output tiles and a long K (the weight gradients dW = dY^T X of the full fine-tune
+ * backward, K = all tokens of the batch): C_s[M,N] (fp32) = A[M, K_s] * W[N, K_s]^T for `planes` consecutive slices K_s
+ * of K, plane s at C + s * plane_stride floats; (split, output tile) pairs are the work items of the persistent kernel.
+ * Returns the number of planes written (>= 1, <= planes) or a negative error code.  vlmclip_sum_planes_f32 adds planes
+ * in index order: out[i] = sum_s parts[s * plane_stride + i] (n and plane_stride multiples of 4). */
+int vlmclip_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,
+                             int64_t plane_stride, int planes, int M, int N, int K, void* stream);
+int vlmclip_sum_planes_f32(const float* parts, int64_t plane_stride, int planes, float* out, int64_t n, void* stream);
 
 /* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */

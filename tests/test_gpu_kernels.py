@@ -69,6 +69,25 @@ def test_gemm(cuda, M, N, K, has_bias, act, has_res, has_stats, out_fp32):
     assert torch.isfinite(out.float()).all()
 
 
+@pytest.mark.parametrize("M,N,K,planes", [(768, 768, 50432, None), (2304, 768, 6304, None), (768, 3072, 6304, 5),
+                                           (100, 264, 1000, 2), (512, 512, 2048, 7), (256, 256, 64, 4)])
+def test_gemm_split_reduction(cuda, M, N, K, planes):
+    """vlmclip_gemm_bf16_splitk + vlmclip_sum_planes_f32 (weight-gradient shapes: few output tiles, long K): equals the
+    unsplit fp32-output GEMM up to the order of the partial sums, and fp32 matmul of the bf16 operands."""
+    from vlm_clip_b200 import ops
+
+    g = _gen(M + N + K)
+    a = (torch.randn(M, K, device=cuda, generator=g) / math.sqrt(K) ** 0.5).to(bf16)
+    w = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K) ** 0.5).to(bf16)
+    out = ops.gemm_splitk(a, w, planes=planes)
+    whole = ops.gemm(a, w, out_fp32=True)
+    ref = a.float() @ w.float().t()
+    assert out.dtype == f32 and out.shape == (M, N)
+    assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    assert _rel(out, whole) < 2e-6, _rel(out, whole)
+    assert torch.equal(out, ops.gemm_splitk(a, w, planes=planes))  # fixed summation order: reproducible
+
+
 def test_gemm_emits_and_consumes_ln_partials(cuda):
     """out-proj style GEMM writes per-32-column (mean, M2) partials of its output rows; an LN-folded GEMM consumes them.
     The pair must equal LayerNorm followed by a plain dense layer."""

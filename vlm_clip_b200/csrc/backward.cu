@@ -139,6 +139,20 @@ cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
   }
 }
 
+// out[i] = sum_s parts[s * stride + i], s in index order (second pass of a split reduction)
+__global__ void __launch_bounds__(256)
+sum_planes_f32_kernel(const float* __restrict__ parts, int64_t stride, int planes, float* __restrict__ out, int64_t n4) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(parts) + i);
+    for (int s = 1; s < planes; ++s) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(parts + (int64_t)s * stride) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+
 // acc[i] += float(b[i]): a bf16 gradient branch joins the fp32 gradient of a skip connection
 __global__ void __launch_bounds__(256)
 add_bf16_into_f32_kernel(float* __restrict__ acc, const __nv_bfloat16* __restrict__ b, int64_t n) {
@@ -450,6 +464,15 @@ extern "C" int vlmclip_cast_f32_to_bf16(const float* src, void* dst, int64_t n, 
   cast_f32_to_bf16_kernel<<<grid_cap((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n,
                                                                                        vec_ok);
   return report_cuda(cudaGetLastError(), "cast_f32_to_bf16_kernel launch");
+}
+
+extern "C" int vlmclip_sum_planes_f32(const float* parts, int64_t plane_stride, int planes, float* out, int64_t n, void* stream) {
+  VLMCLIP_CHECK_ARG(parts && out && planes >= 1 && n > 0 && n % 4 == 0 && plane_stride % 4 == 0,
+                    "sum_planes: n and plane_stride must be positive multiples of 4");
+  VLMCLIP_CHECK_ARG((uintptr_t)parts % 16 == 0 && (uintptr_t)out % 16 == 0, "sum_planes: pointers must be 16-byte aligned");
+  count_launch(1);
+  sum_planes_f32_kernel<<<grid_cap(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(parts, plane_stride, planes, out, n / 4);
+  return report_cuda(cudaGetLastError(), "sum_planes_f32_kernel launch");
 }
 
 extern "C" int vlmclip_add_bf16_into_f32(float* acc, const void* b, int64_t n, void* stream) {

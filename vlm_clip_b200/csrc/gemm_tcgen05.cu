@@ -67,6 +67,11 @@ struct GemmParams {
   int staged;  // 1: residual in / result out go through swizzled smem panels and TMA (bf16 output only)
   int int_pack;
   int m_tiles, n_tiles, k_blocks;
+  // Split of the reduction dimension across work items (weight-gradient GEMMs: few output tiles, K = all tokens):
+  // work item = (split, output tile); split s reduces k-blocks [s * kb_per_split, ...) and writes its own fp32 plane
+  // C + s * split_stride (direct fp32 epilogue only); a second pass adds the planes in index order.  ksplit = 1: off.
+  int ksplit, kb_per_split;
+  int64_t split_stride;
 };
 
 // EB = panel buffers per epilogue group.  EB = 1: one 16 KB panel per group (residual in / result out chained through
@@ -239,16 +244,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_trigger();  // the next kernel in the stream may start its own prologue as SMs free up
 
   // pair: tiles are 256 rows tall (m index counts pair tiles); this CTA's 128-row block is 2*m + rank
-  const int num_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int tiles_mn = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int num_tiles = tiles_mn * p.ksplit;  // work items: (reduction split, output tile)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
     for (int tile = unit; tile < num_tiles; tile += n_units) {
-      const int m_t = tile / p.n_tiles;
-      const int n_blk = tile - m_t * p.n_tiles;
+      const int split = tile / tiles_mn, t_mn = tile - split * tiles_mn;
+      const int m_t = t_mn / p.n_tiles;
+      const int n_blk = t_mn - m_t * p.n_tiles;
       const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (PAIR) {
           // Both CTAs' loads complete on the LEADER's full barrier; the leader alone arrives, expecting the bytes of both
@@ -280,7 +288,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[abuf], aphase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + abuf * BLOCK_N;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint64_t a_desc = make_umma_desc_sw128(smem_u32(sA + stage * L::A_BYTES));
@@ -289,9 +299,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
             if (PAIR)
-              umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             else
-              umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR)
@@ -402,8 +412,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float pf_bias = 0.f, pf_colc = 0.f, pf_mean = 0.f, pf_rstd = 1.f;
     auto prefetch_tile = [&](int tile) {
       if (tile >= num_tiles) return;
-      const int m_t = tile / p.n_tiles;
-      const int n_blk = tile - m_t * p.n_tiles;
+      const int t_mn = tile % tiles_mn;
+      const int m_t = t_mn / p.n_tiles;
+      const int n_blk = t_mn - m_t * p.n_tiles;
       const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
       const int row = m_blk * BLOCK_M + row_in_tile;
       const int col = n_blk * BLOCK_N + et;
@@ -435,8 +446,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = unit; tile < num_tiles; tile += n_units) {
       long long t0 = dbg ? clock64() : 0;
       ++ntl;
-      const int m_t = tile / p.n_tiles;
-      const int n_blk = tile - m_t * p.n_tiles;
+      const int split = tile / tiles_mn, t_mn = tile - split * tiles_mn;
+      const int m_t = t_mn / p.n_tiles;
+      const int n_blk = t_mn - m_t * p.n_tiles;
       const int m_blk = PAIR ? 2 * m_t + (int)cta_rank : m_t;
       const int row = m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
@@ -627,7 +639,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[7] += bf16_hi(rr.w);
               }
               if (p.out_fp32) {
-                float* out = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col;
+                float* out = reinterpret_cast<float*>(p.C) + (int64_t)split * p.split_stride + (int64_t)row * p.ldc + col;
                 *reinterpret_cast<float4*>(out) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(out + 4) = make_float4(v[4], v[5], v[6], v[7]);
               } else {
@@ -683,14 +695,14 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   }
   p.n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   if (!PAIR) {
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(grid), dim3(GEMM_THREADS),
                                   L::DYN_BYTES, stream, 1, tmA, tmB, tmC, tmR, p),
                        "gemm_bf16_tn_kernel launch");
   }
   // CTA pairs: cluster of 2 along x, one pair per two SMs
-  const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.ksplit;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS),
                                 L::DYN_BYTES, stream, 2, tmA, tmB, tmC, tmR, p),
@@ -705,11 +717,11 @@ void count_launch(int n);
 
 using namespace vlmclip;
 
-extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
-                                 const float* bias, const void* residual, int64_t ldr, const float* row_stats,
-                                 const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
-                                 float* stats_part_out, float* stats_out, int32_t* row_counters, int M, int N, int K, int act,
-                                 int out_fp32, void* stream) {
+static int gemm_bf16_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
+                          const void* residual, int64_t ldr, const float* row_stats, const float* col_c,
+                          const float* stats_part_in, int npart_in, float ln_eps, float* stats_part_out, float* stats_out,
+                          int32_t* row_counters, int M, int N, int K, int act, int out_fp32, int splitk_planes,
+                          int64_t splitk_stride, void* stream) {
   VLMCLIP_CHECK_ARG(A && W && C, "gemm: null A/W/C pointer");
   VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dims M=%d N=%d K=%d", M, N, K);
   VLMCLIP_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8 (K=%d N=%d)", K, N);
@@ -755,6 +767,16 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.out_fp32 = out_fp32;
   p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.ksplit = 1;
+  p.kb_per_split = p.k_blocks;
+  p.split_stride = 0;
+  if (splitk_planes > 1) {
+    VLMCLIP_CHECK_ARG(out_fp32 && !bias && !residual && !row_stats && !stats_part_in && !stats_part_out && act == 0,
+                      "gemm: a split reduction needs the plain fp32 output (no bias / residual / LN fold / activation)");
+    p.kb_per_split = (p.k_blocks + splitk_planes - 1) / splitk_planes;
+    p.ksplit = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+    p.split_stride = splitk_stride;
+  }
 
   // Tile width: 256 columns feed the tensor core best (96 B of smem operand traffic per clock against 128 B/clk for a
   // 128-wide tile), but when 256-wide tiles leave the last wave of the persistent grid mostly empty (e.g. N = 512,
@@ -843,6 +865,31 @@ extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 #undef VLMCLIP_GEMM_LAUNCH
 }
 
+extern "C" int vlmclip_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                 const float* bias, const void* residual, int64_t ldr, const float* row_stats,
+                                 const float* col_c, const float* stats_part_in, int npart_in, float ln_eps,
+                                 float* stats_part_out, float* stats_out, int32_t* row_counters, int M, int N, int K, int act,
+                                 int out_fp32, void* stream) {
+  return gemm_bf16_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, row_stats, col_c, stats_part_in, npart_in, ln_eps,
+                        stats_part_out, stats_out, row_counters, M, N, K, act, out_fp32, 1, 0, stream);
+}
+
+// C_s[M,N] (fp32) = A[M, K_s] W[N, K_s]^T for `planes` consecutive slices K_s of the reduction dimension, plane s at
+// C + s * plane_stride floats: the weight-gradient GEMMs of the full-fine-tune backward (dW = dY^T X, K = all tokens)
+// have only a handful of output tiles, so the reduction is what gets distributed over the SMs.  The caller adds the
+// planes in index order (vlmclip_sum_planes_f32): deterministic.  Returns the number of planes actually written
+// (<= planes: no slice is empty), or a negative error code.
+extern "C" int vlmclip_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,
+                                        int64_t plane_stride, int planes, int M, int N, int K, void* stream) {
+  VLMCLIP_CHECK_ARG(planes >= 1 && plane_stride >= (int64_t)(M - 1) * ldc + N, "gemm_splitk: bad planes / plane_stride");
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int per = (k_blocks + planes - 1) / planes;
+  const int used = (k_blocks + per - 1) / per;
+  const int rc = gemm_bf16_impl(A, lda, W, ldw, C, ldc, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 0.f, nullptr, nullptr,
+                                nullptr, M, N, K, 0, 1, planes, plane_stride, stream);
+  return rc != 0 ? (rc > 0 ? -rc : rc) : used;
+}
+
 // x (two planes: hi at X, lo at X + plane_stride) += A W^T + bias, in place; optional LayerNorm partials of the updated
 // rows.  The out-proj / fc2 step of an encoder layer (HF modeling_clip.py:372-383) on the two-term residual stream.
 extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ldw, void* X, int64_t ldx,
@@ -878,6 +925,9 @@ extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W,
   p.staged = 1;
   p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.ksplit = 1;
+  p.kb_per_split = p.k_blocks;
+  p.split_stride = 0;
   static const int dbg_flag = []() {
     const char* e = getenv("VLMCLIP_GEMM_DEBUG");
     return (e != nullptr && e[0] == '1') ? 1 : 0;

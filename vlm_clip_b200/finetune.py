@@ -30,6 +30,9 @@ from . import _native as N
 from . import ops
 
 bf16, f32 = torch.bfloat16, torch.float32
+import os as _os
+
+_SPLITK = _os.environ.get("VLMCLIP_WGRAD_SPLITK", "1") != "0"  # A/B switch of the split-reduction weight-gradient GEMMs
 
 _LAYER_PARAMS = ("layer_norm1.weight", "layer_norm1.bias", "self_attn.q_proj.weight", "self_attn.q_proj.bias",
                  "self_attn.k_proj.weight", "self_attn.k_proj.bias", "self_attn.v_proj.weight", "self_attn.v_proj.bias",
@@ -43,7 +46,8 @@ def _dense_bwd(dy16, x16, W16):
     (dx bf16 [M, K], dW fp32 [N, K], db fp32 [N])."""
     dx = ops.gemm(dy16, ops.transpose_bf16(W16))
     dyT = ops.transpose_bf16(dy16)
-    dW = ops.gemm(dyT, ops.transpose_bf16(x16), out_fp32=True)
+    # few output tiles (N x K of the layer), a 50 k-row reduction: the reduction is what gets spread over the SMs
+    dW = ops.gemm_splitk(dyT, ops.transpose_bf16(x16)) if _SPLITK else ops.gemm(dyT, ops.transpose_bf16(x16), out_fp32=True)
     return dx, dW, ops.rowsum_bf16(dyT)
 
 

@@ -107,6 +107,51 @@ def gemm_res2(a, w, bias, x2, stats_part_out=None, stats_out=None, row_counters=
     return x2
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(dev) -> int:
+    n = _SM_COUNT.get(str(dev))
+    if n is None:
+        n = _SM_COUNT[str(dev)] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return n
+
+
+@_traced
+def gemm_splitk(a, w, planes=None):
+    """fp32 out[M,N] = a[M,K] @ w[N,K]^T with the REDUCTION distributed over the SMs (vlmclip_gemm_bf16_splitk + an
+    in-order sum of the partial planes): for the weight-gradient shapes, M x N = a few output tiles and K = all tokens."""
+    _req(a.dtype == bf16 and w.dtype == bf16 and a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1],
+         "gemm_splitk: a [M, K], w [N, K] bf16")
+    _req(a.stride(1) == 1 and w.stride(1) == 1, "gemm_splitk: operands must be row-major (K contiguous)")
+    M, K = a.shape
+    Nn = w.shape[0]
+    if planes is None:
+        # work items = planes x (256 x 256 pair tiles) on sms / 2 CTA pairs: two per pair when the tiles alone are fewer
+        tiles = ((M + 255) // 256) * ((Nn + 255) // 256)
+        planes = max(1, min(_sm_count(a.device) // tiles, (K + 63) // 64 // 8))
+    if planes <= 1:
+        return gemm(a, w, out_fp32=True)
+    stride = (M * Nn + 3) // 4 * 4
+    parts = torch.empty((planes, stride), device=a.device, dtype=f32)
+    lib = N.load()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    used = lib.vlmclip_gemm_bf16_splitk(N.ptr(a), a.stride(0), N.ptr(w), w.stride(0), N.ptr(parts), Nn, stride, int(planes), M, Nn,
+                                        K, N.stream())
+    if used <= 0:
+        N.check(used if used < 0 else -1, "vlmclip_gemm_bf16_splitk")
+    if prof is not None:
+        e1.record()
+        prof["gemm"].append((e0, e1, 2.0 * M * Nn * K))
+    out = torch.empty((M, Nn), device=a.device, dtype=f32)
+    _req((M * Nn) % 4 == 0, "gemm_splitk: M * N must be a multiple of 4")
+    N.check(lib.vlmclip_sum_planes_f32(N.ptr(parts), stride, int(used), N.ptr(out), M * Nn, N.stream()), "vlmclip_sum_planes_f32")
+    return out
+
+
 @_traced
 def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm: x must be bf16 [M, D]")
