@@ -84,7 +84,9 @@ def test_gemm_split_reduction(cuda, M, N, K, planes):
     ref = a.float() @ w.float().t()
     assert out.dtype == f32 and out.shape == (M, N)
     assert _rel(out, ref) < 2e-5, _rel(out, ref)
-    assert _rel(out, whole) < 2e-6, _rel(out, whole)
+    # the unsplit kernel accumulates all of K in one fp32 TMEM accumulator: at K = 50 k it is the LESS accurate of the two
+    # (5.6e-5 from the split result, which sits 2e-5 from the fp32 matmul)
+    assert _rel(out, whole) < 2e-4, _rel(out, whole)
     assert torch.equal(out, ops.gemm_splitk(a, w, planes=planes))  # fixed summation order: reproducible
 
 
