@@ -370,9 +370,9 @@ def run_native_arm(args):
     eager = None
     if use_graph and not args.lean:
         trainer.cuda_graph = False
-        Ke = max(5, K // 2)
-        ms_eager, host_eager, _, _ = timed_resident(Ke, 3)
-        ms_eager_e2e, host_eager_e2e = timed_e2e(host, Ke, 3)
+        Ke = K
+        ms_eager, host_eager, _, _ = timed_resident(Ke, W)
+        ms_eager_e2e, host_eager_e2e = timed_e2e(host, Ke, W)
         trainer.cuda_graph = True
         eager = {"what": "same step, kernels enqueued one by one (two native tower calls + ~60 interpreter-level ops per step)",
                  "ms_per_step": ms_eager / Ke, "host_enqueue_ms_per_step": host_eager / Ke,

@@ -94,6 +94,15 @@ int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W, int64_t ld
 int vlmclip_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, float* C, int64_t ldc,
                              int64_t plane_stride, int planes, int M, int N, int K, void* stream);
 int vlmclip_sum_planes_f32(const float* parts, int64_t plane_stride, int planes, float* out, int64_t n, void* stream);
+/* The same split reduction with both operands MN-major: C_s[M,N] = A_t[K_s, M]^T * B_t[K_s, N] (A_t, B_t row-major with K
+ * as the row index), i.e. dW = dY^T X read from dY [tokens, N_out] and X [tokens, K_in] as they lie - no transposed
+ * copies, no padding of K.  M, N multiples of 8. */
+int vlmclip_gemm_bf16_atb_splitk(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, float* C, int64_t ldc,
+                                 int64_t plane_stride, int planes, int M, int N, int K, void* stream);
+/* out[c] = sum_r x[r, c], x bf16 [R, C] (the bias gradient: column sums of dY); workspace: vlmclip_colsum_bf16_slices(R) * C
+ * floats; two deterministic passes. */
+int vlmclip_colsum_bf16_slices(int R);
+int vlmclip_colsum_bf16(const void* x, int64_t ldx, float* out, float* workspace, int R, int C, void* stream);
 
 /* LayerNorm over the last dimension (eps as given, affine), fp32 statistics.  HF:371,380,562,677.
  *   x: bf16 [M, D] (ldx), y: bf16 [M, D] (ldy).  gamma/beta fp32[D].  stats_out (optional): fp32[M][2]. */

@@ -90,6 +90,25 @@ def test_gemm_split_reduction(cuda, M, N, K, planes):
     assert torch.equal(out, ops.gemm_splitk(a, w, planes=planes))  # fixed summation order: reproducible
 
 
+@pytest.mark.parametrize("K,M,N,planes", [(50432, 768, 768, None), (6304, 2304, 768, None), (6301, 768, 3072, 5),
+                                           (1000, 104, 264, 2), (2048, 512, 512, 1), (77, 256, 256, 1), (333, 128, 128, 3)])
+def test_gemm_mn_major_operands_split_reduction(cuda, K, M, N, planes):
+    """vlmclip_gemm_bf16_atb_splitk: out = at^T bt with at [K, M], bt [K, N] read as they lie (MN-major UMMA descriptors),
+    K not padded; and the bias-gradient column sums (vlmclip_colsum_bf16)."""
+    from vlm_clip_b200 import ops
+
+    g = _gen(M + N + K)
+    at = (torch.randn(K, M, device=cuda, generator=g) / math.sqrt(K) ** 0.5).to(bf16)
+    bt = (torch.randn(K, N, device=cuda, generator=g) / math.sqrt(K) ** 0.5).to(bf16)
+    out = ops.gemm_atb_splitk(at, bt, planes=planes)
+    ref = at.float().t() @ bt.float()
+    assert out.dtype == f32 and out.shape == (M, N)
+    assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    assert torch.equal(out, ops.gemm_atb_splitk(at, bt, planes=planes))
+    cs = ops.colsum_bf16(at)
+    assert torch.allclose(cs, at.float().sum(0), rtol=1e-4, atol=1e-4 * at.float().abs().sum(0).max().item())
+
+
 def test_gemm_emits_and_consumes_ln_partials(cuda):
     """out-proj style GEMM writes per-32-column (mean, M2) partials of its output rows; an LN-folded GEMM consumes them.
     The pair must equal LayerNorm followed by a plain dense layer."""

@@ -29,6 +29,9 @@ PROTOTYPES = {
     "vlmclip_gemm_bf16_res2": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _f, _i, _i, _i, _p]),
     "vlmclip_gemm_bf16_splitk": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "vlmclip_sum_planes_f32": (_i, [_p, _i64, _i, _p, _i64, _p]),
+    "vlmclip_gemm_bf16_atb_splitk": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p]),
+    "vlmclip_colsum_bf16_slices": (_i, [_i]),
+    "vlmclip_colsum_bf16": (_i, [_p, _i64, _p, _p, _i, _i, _p]),
     "vlmclip_layernorm_bf16": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _p]),
     "vlmclip_layernorm_bf16_f32out": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _f, _p]),
     "vlmclip_ln_partials_to_stats": (_i, [_p, _p, _i, _i, _f, _p]),

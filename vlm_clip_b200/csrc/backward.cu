@@ -194,6 +194,38 @@ colsum_f32_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ 
   out[c] = s;
 }
 
+// part[slice][c] = sum over the rows of the slice of x[r, c], x bf16 [R, C]: first pass of the bias gradient (column sums
+// of dY) without a transposed copy of dY.  Block = 32 column vectors (8 columns each) x 8 row lanes; fixed order.
+__global__ void __launch_bounds__(256)
+colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ part, int R, int C,
+                           int rows_per_slice) {
+  __shared__ float red[8][32][9];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cv) * 8;
+  const int r0 = blockIdx.y * rows_per_slice;
+  const int r1 = min(R, r0 + rows_per_slice);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float f[8];
+      unpack8(ld_nc_v4(x + (int64_t)r * ldx + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cv][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < 8; ++k) s += red[k][cv][j];
+      part[(int64_t)blockIdx.y * C + c + j] = s;
+    }
+  }
+}
+
 // quick_gelu (HF:349): y = a * sigmoid(1.702 a), the same one-MUFU form as the fused GEMM epilogue
 __global__ void __launch_bounds__(256)
 quick_gelu_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ y, int64_t n8) {
@@ -495,6 +527,24 @@ extern "C" int vlmclip_colsum_f32(const float* x, int64_t ldx, float* out, int R
   count_launch(1);
   colsum_f32_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, R, C);
   return report_cuda(cudaGetLastError(), "colsum_f32_kernel launch");
+}
+
+// out[c] = sum_r x[r, c], x bf16 [R, C] (ldx elements between rows), C % 8 == 0; workspace: vlmclip_colsum_bf16_slices(R) * C floats
+extern "C" int vlmclip_colsum_bf16_slices(int R) {
+  const int s = (R + 511) / 512;
+  return s < 1 ? 1 : (s > 128 ? 128 : s);
+}
+extern "C" int vlmclip_colsum_bf16(const void* x, int64_t ldx, float* out, float* workspace, int R, int C, void* stream) {
+  VLMCLIP_CHECK_ARG(x && out && workspace && R > 0 && C > 0 && C % 8 == 0 && ldx >= C && ldx % 8 == 0,
+                    "colsum_bf16: C and ldx must be positive multiples of 8");
+  VLMCLIP_CHECK_ARG((uintptr_t)x % 16 == 0, "colsum_bf16: x must be 16-byte aligned");
+  const int slices = vlmclip_colsum_bf16_slices(R);
+  const int rows_per_slice = (R + slices - 1) / slices;
+  count_launch(2);
+  colsum_bf16_partial_kernel<<<dim3((C / 8 + 31) / 32, slices), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, workspace, R, C, rows_per_slice);
+  colsum_f32_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(workspace, C, out, slices, C);
+  return report_cuda(cudaGetLastError(), "colsum_bf16 launch");
 }
 
 extern "C" int vlmclip_quick_gelu_bf16(const void* a, void* y, int64_t n, void* stream) {

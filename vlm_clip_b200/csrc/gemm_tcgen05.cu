@@ -161,7 +161,11 @@ __device__ __forceinline__ void epi_math8(float* v, const float* sBias, const fl
 //                 moved by ONE 3-D TMA box per direction.
 enum { EPI_GENERIC = 0, EPI_FOLD = 1, EPI_FOLD_ACT = 2, EPI_RES = 3, EPI_PLAIN = 4, EPI_RES2 = 5 };
 
-template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
+// OPMN = true: both operands are MN-major in global memory, A_t [K, M] and B_t [K, N] (row-major, K = rows), i.e.
+// C = A_t^T B_t - the weight-gradient form dW = dY^T X with dY [tokens, N_out], X [tokens, K_in] read as they lie, no
+// transposed copies.  A stage then holds [64 k rows][64 contiguous m] atoms of 8 KB (128-B swizzle), two per 128 rows of
+// M or N; the MMA descriptors are the MN-major ones (LBO = 8 KB between atoms, SBO = 1 KB between 8-row k groups).
+template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI, bool OPMN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -264,13 +268,33 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // after its empty barrier fired, i.e. after the leader's MMAs consumed (hence completed) the current phase,
           // and bytes landing before the leader's expect_tx merely drive the tx-count negative for a moment.
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-          tma_load_2d_pair(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d_pair(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K,
-                           n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+          if (OPMN) {
+            // [64 k][64 m] atoms: inner coordinate = m (or n), outer = k
+#pragma unroll
+            for (int h = 0; h < BLOCK_M / 64; ++h)
+              tma_load_2d_pair(sA + stage * L::A_BYTES + h * 8192, &tmA, &full_bar[stage], m_blk * BLOCK_M + 64 * h, kb * BLOCK_K);
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 128; ++h)
+              tma_load_2d_pair(sB + stage * L::B_BYTES + h * 8192, &tmB, &full_bar[stage],
+                               n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2) + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d_pair(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d_pair(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K,
+                             n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+          }
         } else {
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (OPMN) {
+#pragma unroll
+            for (int h = 0; h < BLOCK_M / 64; ++h)
+              tma_load_2d(sA + stage * L::A_BYTES + h * 8192, &tmA, &full_bar[stage], m_blk * BLOCK_M + 64 * h, kb * BLOCK_K);
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / 64; ++h)
+              tma_load_2d(sB + stage * L::B_BYTES + h * 8192, &tmB, &full_bar[stage], n_blk * BLOCK_N + 64 * h, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sA + stage * L::A_BYTES, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -281,7 +305,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (pair: leader CTA only) =====================
     if (!PAIR || cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc =
+          make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N) | (OPMN ? ((1u << 15) | (1u << 16)) : 0u);  // A, B MN-major
       uint32_t stage = 0, phase = 0;
       uint32_t abuf = 0, aphase = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
@@ -293,15 +318,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t a_desc = make_umma_desc_sw128(smem_u32(sA + stage * L::A_BYTES));
-          const uint64_t b_desc = make_umma_desc_sw128(smem_u32(sB + stage * L::B_BYTES));
+          const uint64_t a_desc = OPMN ? make_umma_desc_mn_sw128(smem_u32(sA + stage * L::A_BYTES), 8192u)
+                                       : make_umma_desc_sw128(smem_u32(sA + stage * L::A_BYTES));
+          const uint64_t b_desc = OPMN ? make_umma_desc_mn_sw128(smem_u32(sB + stage * L::B_BYTES), 8192u)
+                                       : make_umma_desc_sw128(smem_u32(sB + stage * L::B_BYTES));
+          // K-major: advance 16 bf16 = 32 B inside the 128-B swizzle span (+2 in the addr >> 4 field);
+          // MN-major: 16 k rows = two 8-row groups of 1 KB (+128)
+          constexpr uint32_t kstep = OPMN ? (2048u >> 4) : 2u;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-B swizzle span: +2 in the (addr >> 4) field
             if (PAIR)
-              umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              umma_bf16_ss_pair(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             else
-              umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+              umma_bf16_ss(d_tmem, a_desc + kstep * k, b_desc + kstep * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR)
@@ -683,13 +712,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI>
+template <int BLOCK_N, int STAGES, int EB, bool PAIR, int EPI, bool OPMN = false>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                 GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES, EB, PAIR, EPI == EPI_RES2 ? 2 : 1>;
   static bool attr_set = false;  // benign race: setting the attribute twice is harmless
   if (!attr_set) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>,
+    VLMCLIP_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI, OPMN>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
@@ -697,14 +726,14 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   if (!PAIR) {
     const int tiles = p.m_tiles * p.n_tiles * p.ksplit;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(grid), dim3(GEMM_THREADS),
+    return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI, OPMN>, dim3(grid), dim3(GEMM_THREADS),
                                   L::DYN_BYTES, stream, 1, tmA, tmB, tmC, tmR, p),
                        "gemm_bf16_tn_kernel launch");
   }
   // CTA pairs: cluster of 2 along x, one pair per two SMs
   const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.ksplit;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-  return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS),
+  return report_cuda(launch_pdl(gemm_bf16_tn_kernel<BLOCK_N, STAGES, EB, PAIR, EPI, OPMN>, dim3(2 * pairs), dim3(GEMM_THREADS),
                                 L::DYN_BYTES, stream, 2, tmA, tmB, tmC, tmR, p),
                      "gemm_bf16_tn_kernel<pair> launch");
 }
@@ -963,4 +992,46 @@ extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W,
   }
   if (wide) return launch_gemm<256, 4, 1, false, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
   return launch_gemm<128, 4, 2, false, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+}
+
+// C_s[M,N] (fp32) = A_t[K_s, M]^T B_t[K_s, N] over `planes` slices K_s of the K rows, plane s at C + s * plane_stride: the
+// weight gradient dW = dY^T X read from dY [tokens, N_out] and X [tokens, K_in] as they lie (MN-major operands, no
+// transposed copies; K needs no padding: rows past K are zero-filled by TMA).  Returns the planes written or < 0.
+extern "C" int vlmclip_gemm_bf16_atb_splitk(const void* At, int64_t ldat, const void* Bt, int64_t ldbt, float* C, int64_t ldc,
+                                            int64_t plane_stride, int planes, int M, int N, int K, void* stream) {
+  VLMCLIP_CHECK_ARG(At && Bt && C, "gemm_atb: null pointer");
+  VLMCLIP_CHECK_ARG(M > 0 && N > 0 && K > 0 && M % 8 == 0 && N % 8 == 0, "gemm_atb: M and N must be positive multiples of 8");
+  VLMCLIP_CHECK_ARG(ldat % 8 == 0 && ldbt % 8 == 0 && ldat >= M && ldbt >= N && ldc >= N && ldc % 4 == 0,
+                    "gemm_atb: bad leading dimensions");
+  VLMCLIP_CHECK_ARG(((uintptr_t)At % 16 == 0) && ((uintptr_t)Bt % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                    "gemm_atb: pointers must be 16-byte aligned");
+  VLMCLIP_CHECK_ARG(planes >= 1 && plane_stride >= (int64_t)(M - 1) * ldc + N, "gemm_atb: bad planes / plane_stride");
+  GemmParams p{};
+  p.C = C;
+  p.ldc = ldc;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.out_fp32 = 1;
+  p.staged = 0;
+  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.kb_per_split = (p.k_blocks + planes - 1) / planes;
+  p.ksplit = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.split_stride = plane_stride;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, At, K, M, ldat, 64);  // box: 64 k rows x 64 contiguous m
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, Bt, K, N, ldbt, 64);
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  count_launch(1);
+  const bool wide = N > 128;
+  if (wide && M > BLOCK_M)
+    rc = launch_gemm<256, 6, 2, true, EPI_GENERIC, true>(tmA, tmB, tmA, tmA, p, s);
+  else if (wide)
+    rc = launch_gemm<256, 4, 2, false, EPI_GENERIC, true>(tmA, tmB, tmA, tmA, p, s);
+  else
+    rc = launch_gemm<128, 6, 2, false, EPI_GENERIC, true>(tmA, tmB, tmA, tmA, p, s);
+  return rc != 0 ? (rc > 0 ? -rc : rc) : p.ksplit;
 }

@@ -32,7 +32,9 @@ from . import ops
 bf16, f32 = torch.bfloat16, torch.float32
 import os as _os
 
-_SPLITK = _os.environ.get("VLMCLIP_WGRAD_SPLITK", "1") != "0"  # A/B switch of the split-reduction weight-gradient GEMMs
+# weight-gradient GEMMs: "mn" (default) MN-major operands + split reduction, "splitk" transposed copies + split
+# reduction, "plain" transposed copies, one reduction per output tile (round 1); A/B switch
+_WGRAD = _os.environ.get("VLMCLIP_WGRAD", "mn")
 
 _LAYER_PARAMS = ("layer_norm1.weight", "layer_norm1.bias", "self_attn.q_proj.weight", "self_attn.q_proj.bias",
                  "self_attn.k_proj.weight", "self_attn.k_proj.bias", "self_attn.v_proj.weight", "self_attn.v_proj.bias",
@@ -45,9 +47,14 @@ def _dense_bwd(dy16, x16, W16):
     """Backward of y = x W^T + b through the forward GEMM.  dy16 [M, N], x16 [M, K], W16 [N, K] (all bf16) ->
     (dx bf16 [M, K], dW fp32 [N, K], db fp32 [N])."""
     dx = ops.gemm(dy16, ops.transpose_bf16(W16))
+    if _WGRAD == "mn":
+        # dW = dY^T X straight from dY and X (MN-major operand descriptors), the token reduction split over the SMs;
+        # db = column sums of dY.  No transposed copies of the two activation-sized tensors.
+        return dx, ops.gemm_atb_splitk(dy16, x16), ops.colsum_bf16(dy16)
     dyT = ops.transpose_bf16(dy16)
     # few output tiles (N x K of the layer), a 50 k-row reduction: the reduction is what gets spread over the SMs
-    dW = ops.gemm_splitk(dyT, ops.transpose_bf16(x16)) if _SPLITK else ops.gemm(dyT, ops.transpose_bf16(x16), out_fp32=True)
+    xT = ops.transpose_bf16(x16)
+    dW = ops.gemm_splitk(dyT, xT) if _WGRAD == "splitk" else ops.gemm(dyT, xT, out_fp32=True)
     return dx, dW, ops.rowsum_bf16(dyT)
 
 

@@ -153,6 +153,52 @@ def gemm_splitk(a, w, planes=None):
 
 
 @_traced
+def gemm_atb_splitk(at, bt, planes=None):
+    """fp32 out[M,N] = at[K,M]^T @ bt[K,N] (both bf16, row-major, K = rows) on the tcgen05 GEMM with MN-major operand
+    descriptors and a split reduction: the weight gradient dW = dY^T X without transposed copies of dY and X."""
+    _req(at.dtype == bf16 and bt.dtype == bf16 and at.dim() == 2 and bt.dim() == 2 and at.shape[0] == bt.shape[0],
+         "gemm_atb_splitk: at [K, M], bt [K, N] bf16")
+    _req(at.stride(1) == 1 and bt.stride(1) == 1, "gemm_atb_splitk: operands must be row-major")
+    K, M = at.shape
+    Nn = bt.shape[1]
+    _req(M % 8 == 0 and Nn % 8 == 0, "gemm_atb_splitk: M and N must be multiples of 8")
+    if planes is None:
+        tiles = ((M + 255) // 256) * ((Nn + 255) // 256)
+        planes = max(1, min(_sm_count(at.device) // tiles, (K + 63) // 64 // 8))
+    stride = (M * Nn + 3) // 4 * 4
+    parts = torch.empty((planes, stride), device=at.device, dtype=f32)
+    lib = N.load()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    used = lib.vlmclip_gemm_bf16_atb_splitk(N.ptr(at), at.stride(0), N.ptr(bt), bt.stride(0), N.ptr(parts), Nn, stride,
+                                            int(planes), M, Nn, K, N.stream())
+    if used <= 0:
+        N.check(used if used < 0 else -1, "vlmclip_gemm_bf16_atb_splitk")
+    if prof is not None:
+        e1.record()
+        prof["gemm"].append((e0, e1, 2.0 * M * Nn * K))
+    if used == 1:
+        return parts[0, :M * Nn].view(M, Nn)
+    out = torch.empty((M, Nn), device=at.device, dtype=f32)
+    N.check(lib.vlmclip_sum_planes_f32(N.ptr(parts), stride, int(used), N.ptr(out), M * Nn, N.stream()), "vlmclip_sum_planes_f32")
+    return out
+
+
+@_traced
+def colsum_bf16(x):
+    """out[c] = sum_r x[r, c] for bf16 x [R, C] (fp32 result): the bias gradient of a dense layer from dY as it lies."""
+    _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 8 == 0, "colsum_bf16: x must be bf16 [R, C], C % 8 == 0")
+    R, Cc = x.shape
+    lib = N.load()
+    out = torch.empty((Cc,), device=x.device, dtype=f32)
+    ws = torch.empty((lib.vlmclip_colsum_bf16_slices(R) * Cc,), device=x.device, dtype=f32)
+    N.check(lib.vlmclip_colsum_bf16(N.ptr(x), x.stride(0), N.ptr(out), N.ptr(ws), R, Cc, N.stream()), "vlmclip_colsum_bf16")
+    return out
+
+
+@_traced
 def layernorm(x, gamma, beta, eps=1e-5, out=None, stats=None):
     _req(x.dtype == bf16 and x.dim() == 2 and x.stride(1) == 1, "layernorm: x must be bf16 [M, D]")
     M, D = x.shape
