@@ -15,8 +15,13 @@ def test_two_rank_nccl_step_matches_single_process(cuda):
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    import socket
+
     worker = Path(__file__).resolve().parent / "dp_nccl_worker.py"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29611", str(worker)], capture_output=True, text=True, env=env, timeout=900)
+                        "127.0.0.1", "--master-port", str(port), str(worker)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
