@@ -2,7 +2,8 @@
 import os, sys, torch
 sys.path.insert(0, ".")
 from vlm_clip_b200 import ops
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
 dev = torch.device("cuda:0")
@@ -17,10 +18,10 @@ def t_attn(n=20):
     for _ in range(n): ops.attention(qkv, B, S, H, out=out)
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
-clip = O.build_hf_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
+clip = random_init_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
 model = CLIPWithAdapters(clip=clip, use_shared_adapters=False).to(dev)
 trainer = CLIPAdapterTrainer(model, train_dataloader=[None], output_dir="/tmp/ab_ckpt")
-pix, ids, mask = O.synthetic_batch(B)
+pix, ids, mask = synthetic_batch(B)
 batch = {"pixel_values": pix.to(dev), "input_ids": ids.to(dev), "attention_mask": mask.to(dev)}
 torch.cuda.synchronize()
 ready = torch.cuda.Event(); ready.record(); batch["inputs_ready"] = ready

@@ -8,13 +8,14 @@ sys.path.insert(0, ".")
 from vlm_clip_b200 import ops
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import flops_per_pair, random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 
 L14 = "openai/clip-vit-large-patch14"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
-clip = O.build_hf_clip(L14, seed=0).to(dev)
+clip = random_init_clip(L14, seed=0).to(dev)
 for p in clip.parameters():
     p.requires_grad_(False)
 torch.manual_seed(1)
@@ -38,7 +39,7 @@ for i in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
-fl = O.flops_per_pair(L14)
+fl = flops_per_pair(L14)
 res = {"workload": "config 3 per-GPU share: ViT-L/14 + PE-CLIP adapters, Track-M train step", "batch_per_gpu": B,
        "ms_per_step": ms, "images_per_s_per_gpu": B / ms * 1e3, "step_tflops": fl["pair"] * B / ms / 1e9,
        "frac_of_sustained_peak_1356.7": fl["pair"] * B / ms / 1e9 / 1356.7, "loss": loss.item(),

@@ -7,14 +7,15 @@ import torch
 sys.path.insert(0, ".")
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import flops_per_pair, random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 
 B16 = "openai/clip-vit-base-patch16"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 dev = torch.device("cuda:0")
-clip = O.build_hf_clip(B16, seed=0).to(dev)
+clip = random_init_clip(B16, seed=0).to(dev)
 for p in clip.parameters():
     p.requires_grad_(False)
 torch.manual_seed(1)
@@ -27,7 +28,7 @@ common = {"input_ids": ids.to(dev), "attention_mask": torch.ones(B, 77, dtype=to
 clips_f = torch.randn(B, 3, T, 224, 224, generator=g).to(dev)
 clips_u8 = torch.randint(0, 256, (B, T, 360, 480, 3), generator=g, dtype=torch.uint8).to(dev)
 tr = CLIPAdapterTrainer(model, [None], output_dir="/tmp/vlmclip_cfg4")
-fl = O.flops_per_pair(B16)
+fl = flops_per_pair(B16)
 res = {"workload": "config 4: ViT-B/16 + adapters, video clips with temporal mean-pool, Track-M train step", "clips": B,
        "frames_per_clip": T}
 for tag, pix in (("float_clips", clips_f), ("uint8_frames_360x480", clips_u8)):

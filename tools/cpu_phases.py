@@ -1,16 +1,17 @@
 """Host-side time of each phase of training_step (no synchronisation added): finds calls that block on the GPU."""
 import sys, time, torch
 sys.path.insert(0, ".")
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
 from vlm_clip_b200.dist import allreduce_sum_
 dev = torch.device("cuda:0")
 B = 256
-clip = O.build_hf_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
+clip = random_init_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
 model = CLIPWithAdapters(clip=clip, use_shared_adapters=False).to(dev)
 trainer = CLIPAdapterTrainer(model, train_dataloader=[None], output_dir="/tmp/ab_ckpt")
-pix, ids, mask = O.synthetic_batch(B)
+pix, ids, mask = synthetic_batch(B)
 batch = {"pixel_values": pix.to(dev), "input_ids": ids.to(dev), "attention_mask": mask.to(dev)}
 torch.cuda.synchronize()
 ready = torch.cuda.Event(); ready.record()

@@ -7,16 +7,17 @@ sys.path.insert(0, ".")
 from vlm_clip_b200 import ops
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import flops_per_pair, random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
-clip = O.build_hf_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
+clip = random_init_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
 model = CLIPWithAdapters(clip=clip, freeze_clip=False, use_text_adapter=False, use_vision_adapter=False,
                          use_shared_adapters=False).to(dev)
 model.train()
-pix, ids, mask = O.synthetic_batch(B, seed=2)
+pix, ids, mask = synthetic_batch(B, seed=2)
 ids[:, 0] = torch.arange(B) % 1000 + 5
 batch = {"input_ids": ids.to(dev), "attention_mask": mask.to(dev), "pixel_values": pix.to(dev).to(torch.bfloat16)}
 tr = CLIPAdapterTrainer(model, [batch], learning_rate=1e-7, output_dir="/tmp/vlmclip_ft_bench", trainable="all")
@@ -30,7 +31,7 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
-fl = O.flops_per_pair("openai/clip-vit-base-patch16")
+fl = flops_per_pair("openai/clip-vit-base-patch16")
 res = {"workload": "CLIP ViT-B/16 full fine-tune (adapters disabled), Track-M step", "batch": B, "ms_per_step": ms,
        "images_per_s": B / ms * 1e3, "loss": loss.item(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
 try:

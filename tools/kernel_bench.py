@@ -4,7 +4,8 @@ import sys, time, json
 import torch
 sys.path.insert(0, ".")
 from vlm_clip_b200 import ops, _native as N
-from oracle import clip_oracle as O
+from vlm_clip_b200.configs import random_init_clip
+from vlm_clip_b200.data import synthetic_batch
 
 dev = torch.device("cuda:0")
 bf16 = torch.bfloat16
@@ -82,11 +83,11 @@ print(f"im2col            {t6*1e3:8.1f} us  {(pix.numel()*4+B*196*768*2)/t6/1e6:
 # whole model step
 from vlm_clip_b200.model_m import CLIPWithAdapters
 from vlm_clip_b200.trainer import CLIPAdapterTrainer
-clip = O.build_hf_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
+clip = random_init_clip("openai/clip-vit-base-patch16", seed=0).to(dev)
 torch.manual_seed(1)
 model = CLIPWithAdapters(clip=clip, use_shared_adapters=False).to(dev)
 model.train()
-pixs, ids, mask = O.synthetic_batch(B)
+pixs, ids, mask = synthetic_batch(B)
 batch = {"input_ids": ids.to(dev), "attention_mask": mask.to(dev), "pixel_values": pixs.to(dev)}
 tr = CLIPAdapterTrainer(model, [None], output_dir="/tmp/vlmclip_kb")
 n0 = N.launch_count()

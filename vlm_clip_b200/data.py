@@ -98,3 +98,9 @@ class SyntheticPairs(torch.utils.data.Dataset):
 
     def __getitem__(self, i):
         return {"input_ids": self.ids[i], "attention_mask": self.mask[i], "pixel_values": self.pix[i]}
+
+
+def synthetic_batch(batch: int, seed: int = 2, seq: int = 77, image: int = 224):
+    """One batch of SURVEY.md §8d's synthetic inputs as tensors: (pixel_values [B,3,H,W] fp32, input_ids [B,S], mask [B,S])."""
+    d = SyntheticPairs(batch, seed=seed, image=image, seq=seq)
+    return d.pix, d.ids, d.mask
