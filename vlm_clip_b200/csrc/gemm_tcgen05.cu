@@ -987,7 +987,9 @@ extern "C" int vlmclip_gemm_bf16_res2(const void* A, int64_t lda, const void* W,
   count_launch(1);
   if (pair) {
     if (cfg == 43) return launch_gemm<256, 4, 3, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
-    if (cfg == 61) return launch_gemm<256, 6, 1, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
+    // long K (fc2: 48-64 k-blocks per tile): the main loop hides one panel chain per group, the sixth stage pays more
+    // (B/16 fc2 172.0 vs 176.2 us, L/14 fc2 814 vs 828 us); short K (out-proj) needs the second panel (84 vs 104 us)
+    if (cfg == 61 || (cfg == 0 && K >= 2048)) return launch_gemm<256, 6, 1, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
     return launch_gemm<256, 5, 2, true, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
   }
   if (wide) return launch_gemm<256, 4, 1, false, EPI_RES2>(tmA, tmB, tmX, tmX, p, s);
