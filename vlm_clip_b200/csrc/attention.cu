@@ -41,6 +41,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// MASKED = false: no causal / key-padding mask (vision): keys >= S are the only thing to exclude, and only the last
+// 16-key group can contain them - the per-key mask loads and selects disappear from every other group.
+template <bool MASKED>
 __global__ void __launch_bounds__(256, 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                      const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad) {
@@ -135,11 +138,16 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = k0 + nt * 8 + tq * 2 + e;
-          const bool kv = sMask[key] != 0;
-          const bool va = kv && (!causal || key <= row_a);
-          const bool vb = kv && (!causal || key <= row_b);
-          s[nt][e] = va ? s[nt][e] : -INFINITY;
-          s[nt][2 + e] = vb ? s[nt][2 + e] : -INFINITY;
+          if (MASKED) {
+            const bool kv = sMask[key] != 0;
+            const bool va = kv && (!causal || key <= row_a);
+            const bool vb = kv && (!causal || key <= row_b);
+            s[nt][e] = va ? s[nt][e] : -INFINITY;
+            s[nt][2 + e] = vb ? s[nt][2 + e] : -INFINITY;
+          } else if (k0 + nt * 8 + 8 > S) {  // warp-uniform: only the group that straddles S has invalid keys
+            s[nt][e] = key < S ? s[nt][e] : -INFINITY;
+            s[nt][2 + e] = key < S ? s[nt][2 + e] : -INFINITY;
+          }
           bm_a = fmaxf(bm_a, s[nt][e]);
           bm_b = fmaxf(bm_b, s[nt][2 + e]);
         }
@@ -152,8 +160,8 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
     const float mu_a = mn_a == -INFINITY ? 0.f : mn_a;  // fully-masked-so-far rows stay finite
     const float mu_b = mn_b == -INFINITY ? 0.f : mn_b;
-    const float corr_a = exp2f((m_a - mu_a) * scale_log2e);
-    const float corr_b = exp2f((m_b - mu_b) * scale_log2e);
+    const float corr_a = fast_exp2((m_a - mu_a) * scale_log2e);
+    const float corr_b = fast_exp2((m_b - mu_b) * scale_log2e);
     m_a = mn_a;
     m_b = mn_b;
     l_a *= corr_a;
@@ -175,10 +183,10 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int nt = kk * 2 + half;
-          p[half * 4 + 0] = exp2f(fmaf(s[nt][0], scale_log2e, -off_a));
-          p[half * 4 + 1] = exp2f(fmaf(s[nt][1], scale_log2e, -off_a));
-          p[half * 4 + 2] = exp2f(fmaf(s[nt][2], scale_log2e, -off_b));
-          p[half * 4 + 3] = exp2f(fmaf(s[nt][3], scale_log2e, -off_b));
+          p[half * 4 + 0] = fast_exp2(fmaf(s[nt][0], scale_log2e, -off_a));
+          p[half * 4 + 1] = fast_exp2(fmaf(s[nt][1], scale_log2e, -off_a));
+          p[half * 4 + 2] = fast_exp2(fmaf(s[nt][2], scale_log2e, -off_b));
+          p[half * 4 + 3] = fast_exp2(fmaf(s[nt][3], scale_log2e, -off_b));
         }
         l_a += p[0] + p[1] + p[4] + p[5];
         l_b += p[2] + p[3] + p[6] + p[7];
@@ -231,15 +239,20 @@ int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, 
   const int qw = (nblocks + groups - 1) / groups;
   const int Spad = (S + 15) / 16 * 16;
   const size_t smem = (size_t)Spad * KSTRIDE * 2 * 2 + Spad;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  const bool masked = causal != 0 || key_mask != nullptr;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > smem_set[masked ? 1 : 0]) {
+    if (masked)
+      VLMCLIP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      VLMCLIP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[masked ? 1 : 0] = smem;
   }
   dim3 grid(B * H, groups);
   count_launch(1);
-  return report_cuda(launch_pdl(attention_fwd_kernel, grid, dim3(qw * 32), smem, stream, 1, (const __nv_bfloat16*)qkv,
-                                (__nv_bfloat16*)out, key_mask, S, H, causal, scale * 1.4426950408889634f, Spad),
+  auto kern = masked ? attention_fwd_kernel<true> : attention_fwd_kernel<false>;
+  return report_cuda(launch_pdl(kern, grid, dim3(qw * 32), smem, stream, 1, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out,
+                                key_mask, S, H, causal, scale * 1.4426950408889634f, Spad),
                      "attention_fwd_kernel launch");
 }
 

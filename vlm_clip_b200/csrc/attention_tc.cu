@@ -57,6 +57,11 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
     const char* e = getenv("VLMCLIP_ATTN_FORCE_TC");
     return e != nullptr && e[0] == '1';
   }();
+  static const bool force_mma = []() {  // A/B switch: every shape on the register-resident mma.sync kernel
+    const char* e = getenv("VLMCLIP_ATTN_FORCE_MMA");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (force_mma) return attention_fwd_mma_sync(qkv, out, key_mask, B, S, H, causal, scale, s);
   if (workspace != nullptr && split_eligible(S, causal, key_mask))
     return attention_fwd_pingpong_split(qkv, out, workspace, B, S, H, scale, split_variant(), s);
   if (S > 224 || (!force_tc && (causal != 0 || key_mask != nullptr) && S <= 128))
