@@ -726,10 +726,11 @@ def test_attention_key_range_split_merge(cuda, S, lo, hi):
     assert _rel(out, out2.float()) < 8e-3
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 def test_attention_key_range_split_variants_subprocess(variant):
     """VLMCLIP_ATTN_SPLIT selects the variant of the split (1: every row on the tcgen05 kernel, per-thread merge loads;
-    2: tail rows on the single-query kernel, staged merge; 3: every row on the tcgen05 kernel, staged merge).  The switch
+    2: tail rows on the single-query kernel, staged merge; 3: every row on the tcgen05 kernel, staged merge; 4: full
+    128-row tiles on the tcgen05 kernel, the tail rows as one 16-row block per unit on the mma.sync kernel).  The switch
     is read once per process, so each variant is held to the oracle in a fresh one."""
     import os
     import subprocess

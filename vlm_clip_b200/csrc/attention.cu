@@ -46,7 +46,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 template <bool MASKED>
 __global__ void __launch_bounds__(256, 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                     const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad) {
+                     const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad,
+                     int q_begin) {
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_wait();
   pdl_trigger();
@@ -83,7 +84,9 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   cp_async_wait_all();
   __syncthreads();
 
-  const int q0 = (blockIdx.y * nwarps + warp) * 16;
+  // q_begin > 0: only the query rows from q_begin on (the tail rows of a sequence whose full 128-row tiles run on the
+  // tcgen05 kernel); every warp helped to stage K / V above, warps without rows leave here
+  const int q0 = q_begin + (blockIdx.y * nwarps + warp) * 16;
   if (q0 >= S) return;  // no block-wide synchronisation below this point
 
   const int quad = lane >> 2;
@@ -230,13 +233,12 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 namespace vlmclip {
 
-// mma.sync fallback used for S > 256 (ViT-L/14, S = 257), where the single-pass tcgen05 kernel's N <= 256 limit
-// does not hold; same contract as vlmclip_attention_fwd.
-int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
-                           float scale, cudaStream_t stream) {
-  const int nblocks = (S + 15) / 16;
+int attention_fwd_mma_sync_rows(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
+                                float scale, int q_begin, cudaStream_t stream) {
+  const int nblocks = (S - q_begin + 15) / 16;  // 16-row query blocks from q_begin on
   const int groups = (nblocks + 7) / 8;
-  const int qw = (nblocks + groups - 1) / groups;
+  int qw = (nblocks + groups - 1) / groups;
+  if (qw < 4) qw = 4;  // at least four warps stage K and V (warps without query rows exit after the staging)
   const int Spad = (S + 15) / 16 * 16;
   const size_t smem = (size_t)Spad * KSTRIDE * 2 * 2 + Spad;
   const bool masked = causal != 0 || key_mask != nullptr;
@@ -252,8 +254,15 @@ int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, 
   count_launch(1);
   auto kern = masked ? attention_fwd_kernel<true> : attention_fwd_kernel<false>;
   return report_cuda(launch_pdl(kern, grid, dim3(qw * 32), smem, stream, 1, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out,
-                                key_mask, S, H, causal, scale * 1.4426950408889634f, Spad),
+                                key_mask, S, H, causal, scale * 1.4426950408889634f, Spad, q_begin),
                      "attention_fwd_kernel launch");
+}
+
+// mma.sync fallback used for S > 256 (ViT-L/14, S = 257) when the caller gives no workspace for the tcgen05 key-range
+// split, and for the short causal text sequences; same contract as vlmclip_attention_fwd.
+int attention_fwd_mma_sync(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
+                           float scale, cudaStream_t stream) {
+  return attention_fwd_mma_sync_rows(qkv, out, key_mask, B, S, H, causal, scale, 0, stream);
 }
 
 }  // namespace vlmclip

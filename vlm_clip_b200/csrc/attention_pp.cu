@@ -34,6 +34,9 @@ void count_launch(int n);
 int attention_1q_strided(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_row_stride,
                          int64_t kv_batch_stride, void* out, int64_t out_stride, int B, int S, int H, float scale,
                          cudaStream_t stream);
+// attention.cu: register-resident mma.sync kernel restricted to the query rows from q_begin on
+int attention_fwd_mma_sync_rows(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
+                                float scale, int q_begin, cudaStream_t stream);
 
 namespace {
 
@@ -726,13 +729,18 @@ constexpr int PP_MAX_TAIL_ROWS = 2;
 int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, int B, int S, int H, float scale,
                                  int variant, cudaStream_t s) {
   const int tail = S % PP_M;
-  const int Sq = (variant == 2 && tail >= 1 && tail <= PP_MAX_TAIL_ROWS) ? S - tail : S;
+  // variant 4: a sequence a few rows longer than a multiple of 128 (257 = 2 * 128 + 1) keeps its full tiles on the
+  // tcgen05 kernel and sends the tail rows to the mma.sync kernel (one 16-row block per unit) instead of spending a
+  // third 128-row tile slot of BOTH launches on them
+  const bool tail_mma = variant == 4 && tail >= 1 && tail <= 16;
+  const int Sq = ((variant == 2 && tail >= 1 && tail <= PP_MAX_TAIL_ROWS) || tail_mma) ? S - tail : S;
   float2* stats = reinterpret_cast<float2*>(workspace);
   int rc = launch_range(qkv, out, nullptr, B, S, Sq, H, 0, scale, 0, PP_SPLIT_KEYS, stats, 0, s);
   if (rc) return rc;
   rc = launch_range(qkv, out, nullptr, B, S, Sq, H, 0, scale, PP_SPLIT_KEYS, S - PP_SPLIT_KEYS, stats,
                     variant == 1 ? 1 : 2, s);
   if (rc) return rc;
+  if (tail_mma) return attention_fwd_mma_sync_rows(qkv, out, nullptr, B, S, H, 0, scale, Sq, s);
   const int64_t D = (int64_t)H * PP_HD;
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
   for (int r = Sq; r < S; ++r) {

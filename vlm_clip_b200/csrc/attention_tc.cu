@@ -22,12 +22,12 @@ int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, i
 
 using namespace vlmclip;
 
-// VLMCLIP_ATTN_SPLIT: 0 keeps S > 224 on the mma.sync kernel, 1 / 2 / 3 select the variant of the key-range split
+// VLMCLIP_ATTN_SPLIT: 0 keeps S > 224 on the mma.sync kernel, 1 / 2 / 3 / 4 select the variant of the key-range split
 // (attention_pp.cu: attention_fwd_pingpong_split); A/B switch, read once
 static int split_variant() {
   static const int variant = []() {
     const char* e = getenv("VLMCLIP_ATTN_SPLIT");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3;
   }();
   return variant;
 }
