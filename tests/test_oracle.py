@@ -266,3 +266,24 @@ def test_shared_mhs_adapter_matches_executed_reference():
     y = O.shared_mhs_adapter(xt, table, a)
     assert torch.allclose(y[:, :2, :], gold["y_tok01"], atol=2e-5, rtol=1e-5)
     assert abs(y.double().abs().sum().item() - gold["y_abs_sum"]) / gold["y_abs_sum"] < 1e-6
+
+
+def test_rounding_point_emulation_orders_the_residual_layouts():
+    """oracle/emulate_bf16.py (the CPU replay of the CUDA pipeline's rounding points that DESIGN.md §4 quotes): with the
+    same bf16 operand roundings, a one-plane bf16 residual stream must be measurably worse than the two-term (hi + lo)
+    stream, and the two-term stream indistinguishable from an fp32 one."""
+    from oracle import emulate_bf16 as E
+
+    torch.manual_seed(0)
+    clip = O.build_hf_clip(B32, seed=0, vision_layers=4, text_layers=4)
+    sd = {k: v.detach() for k, v in clip.state_dict().items()}
+    pix, ids, mask = O.synthetic_batch(2, seed=2)
+    with torch.no_grad():
+        ref = O.vision_tower(sd, pix, 12)
+        err = {m: E._rel(E.vision_tower(sd, pix, 12, m), ref) for m in ("bf16", "hilo", "fp32")}
+        ref_t = O.text_tower(sd, ids, mask, 8)
+        err_t = {m: E._rel(E.text_tower(sd, ids, mask, 8, m), ref_t) for m in ("bf16", "hilo")}
+    assert err["hilo"] < 0.75 * err["bf16"], err
+    assert abs(err["hilo"] - err["fp32"]) < 0.1 * err["fp32"], err
+    assert err_t["hilo"] < err_t["bf16"], err_t
+    assert err["bf16"] < 2e-2 and err_t["bf16"] < 2e-2  # sanity: all of them are bf16-sized errors
