@@ -7,6 +7,8 @@
 // softmax held in registers; quad reductions by warp shuffles.  Scores and probabilities never touch HBM.
 // This is the mma.sync m16n8k16 (fp32 accumulate) variant.  The tcgen05 kernel in attention_tc.cu serves S <= 256;
 // this one remains for longer sequences (ViT-L/14, S = 257) and as an independent implementation for tests.
+#include <cstdlib>
+
 #include "../../include/vlmclip.h"
 #include "common.cuh"
 
@@ -43,8 +45,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 // MASKED = false: no causal / key-padding mask (vision): keys >= S are the only thing to exclude, and only the last
 // 16-key group can contain them - the per-key mask loads and selects disappear from every other group.
-template <bool MASKED>
-__global__ void __launch_bounds__(256, 2)
+// WIDE = true: one CTA of up to 18 warps covers ALL query blocks of a (batch, head) unit (S <= 288), so K and V are staged
+// once per unit instead of once per group of 8 query blocks (ViT-L/14: 3 x less staging traffic, 17 instead of 12
+// resident warps per SM); the register cap is then 113 per thread.
+template <bool MASKED, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 576 : 256, WIDE ? 1 : 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                      const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad,
                      int q_begin) {
@@ -236,23 +241,28 @@ namespace vlmclip {
 int attention_fwd_mma_sync_rows(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                                 float scale, int q_begin, cudaStream_t stream) {
   const int nblocks = (S - q_begin + 15) / 16;  // 16-row query blocks from q_begin on
-  const int groups = (nblocks + 7) / 8;
+  static const bool wide_ok = []() {  // A/B switch: VLMCLIP_ATTN_MMA_WIDE=0 keeps groups of 8 query blocks per CTA
+    const char* e = getenv("VLMCLIP_ATTN_MMA_WIDE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool wide = wide_ok && nblocks > 8 && nblocks <= 18;
+  const int groups = wide ? 1 : (nblocks + 7) / 8;
   int qw = (nblocks + groups - 1) / groups;
   if (qw < 4) qw = 4;  // at least four warps stage K and V (warps without query rows exit after the staging)
   const int Spad = (S + 15) / 16 * 16;
   const size_t smem = (size_t)Spad * KSTRIDE * 2 * 2 + Spad;
   const bool masked = causal != 0 || key_mask != nullptr;
-  static size_t smem_set[2] = {0, 0};
-  if (smem > smem_set[masked ? 1 : 0]) {
-    if (masked)
-      VLMCLIP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      VLMCLIP_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[masked ? 1 : 0] = smem;
+  using KernT = void (*)(const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*, int, int, int, float, int, int);
+  KernT kern = wide ? (masked ? (KernT)attention_fwd_kernel<true, true> : (KernT)attention_fwd_kernel<false, true>)
+                    : (masked ? (KernT)attention_fwd_kernel<true, false> : (KernT)attention_fwd_kernel<false, false>);
+  static size_t smem_set[4] = {0, 0, 0, 0};
+  const int vi = (wide ? 2 : 0) + (masked ? 1 : 0);
+  if (smem > smem_set[vi]) {
+    VLMCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[vi] = smem;
   }
   dim3 grid(B * H, groups);
   count_launch(1);
-  auto kern = masked ? attention_fwd_kernel<true> : attention_fwd_kernel<false>;
   return report_cuda(launch_pdl(kern, grid, dim3(qw * 32), smem, stream, 1, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out,
                                 key_mask, S, H, causal, scale * 1.4426950408889634f, Spad, q_begin),
                      "attention_fwd_kernel launch");

@@ -1,8 +1,8 @@
 // Attention entry point of the C ABI: out = softmax(q k^T * scale + mask) v, head_dim 64.
 //   HF modeling_clip.py:261-279 (eager_attention_forward), :318-331 (dispatch), :546-551 (causal + padding mask)
 // Dispatches between the tcgen05 ping-pong kernel (attention_pp.cu; S <= 224, the vision tower), its two-launch
-// key-range split (224 < S <= 384 without a mask: ViT-L/14, needs the caller's workspace) and the mma.sync kernel
-// (attention.cu; short causal / masked text sequences and everything else).
+// key-range split (288 < S <= 384 without a mask, needs the caller's workspace) and the mma.sync kernel (attention.cu;
+// short causal / masked text sequences, ViT-L/14's S = 257 in one wide CTA per head, and everything else).
 #include <cstdio>
 #include <cstdlib>
 
@@ -22,18 +22,21 @@ int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, i
 
 using namespace vlmclip;
 
-// VLMCLIP_ATTN_SPLIT: 0 keeps S > 224 on the mma.sync kernel, 1 / 2 / 3 / 4 select the variant of the key-range split
-// (attention_pp.cu: attention_fwd_pingpong_split); A/B switch, read once
+// VLMCLIP_ATTN_SPLIT: unset = auto (224 < S <= 288 on the wide mma.sync kernel, which measures 894 us against the
+// split's 918 us at ViT-L/14, B=512; 288 < S <= 384 on split variant 3), 0 keeps every S > 224 on the mma.sync kernel,
+// 1 / 2 / 3 / 4 force that variant of the key-range split (attention_pp.cu: attention_fwd_pingpong_split) for all
+// 224 < S <= 384; A/B switch, read once
 static int split_variant() {
   static const int variant = []() {
     const char* e = getenv("VLMCLIP_ATTN_SPLIT");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
   }();
   return variant;
 }
 
 static bool split_eligible(int S, int causal, const uint8_t* key_mask) {
-  return split_variant() != 0 && S > 224 && S <= 384 && causal == 0 && key_mask == nullptr;
+  const int v = split_variant();
+  return v != 0 && S > (v < 0 ? 288 : 224) && S <= 384 && causal == 0 && key_mask == nullptr;
 }
 
 extern "C" int64_t vlmclip_attention_fwd_workspace(int B, int S, int H) {
@@ -49,8 +52,9 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
   VLMCLIP_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0, "attention: pointers must be 16-byte aligned");
   VLMCLIP_CHECK_ARG((uintptr_t)workspace % 8 == 0, "attention: workspace must be 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  // Dispatch.  ViT-L/14 (S = 257) exceeds the two-S-buffer TMEM map of the tcgen05 kernel: with a workspace it runs as
-  // two key ranges merged in the second launch's epilogue, without one on the mma.sync kernel.  For the short causal
+  // Dispatch.  S > 224 exceeds the two-S-buffer TMEM map of the tcgen05 kernel: up to S = 288 (ViT-L/14) the wide
+  // mma.sync kernel is the faster of the two measured options, beyond that it runs as two key ranges merged in the second
+  // launch's epilogue (needs the workspace).  For the short causal
   // text sequences (S = 77: 60 % of a 128-row tile would be padding, every chunk takes the masked path) the mma.sync
   // variant measures faster on B200 (43 us vs 98 us at B=256, H=8); VLMCLIP_ATTN_FORCE_TC=1 forces the tcgen05 kernel.
   static const bool force_tc = []() {
@@ -63,7 +67,7 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
   }();
   if (force_mma) return attention_fwd_mma_sync(qkv, out, key_mask, B, S, H, causal, scale, s);
   if (workspace != nullptr && split_eligible(S, causal, key_mask))
-    return attention_fwd_pingpong_split(qkv, out, workspace, B, S, H, scale, split_variant(), s);
+    return attention_fwd_pingpong_split(qkv, out, workspace, B, S, H, scale, split_variant() < 0 ? 3 : split_variant(), s);
   if (S > 224 || (!force_tc && (causal != 0 || key_mask != nullptr) && S <= 128))
     return attention_fwd_mma_sync(qkv, out, key_mask, B, S, H, causal, scale, s);
   return attention_fwd_pingpong(qkv, out, key_mask, B, S, H, causal, scale, s);
