@@ -698,7 +698,7 @@ def test_attention_late_maximum_rescale(cuda, S, late):
                                      (257, 256, 257), (384, 300, 384), (225, 224, 225)])
 def test_attention_key_range_split_merge(cuda, S, lo, hi):
     """288 < S <= 384 (and, with VLMCLIP_ATTN_SPLIT=1..4, every 224 < S <= 384: the subprocess test below) runs as two key
-    ranges ([0, 208) and [208, S)) merged in the second launch's epilogue; 224 < S <= 288 defaults to the wide mma.sync
+    ranges ([0, 208) and [208, S)) merged in the second launch's epilogue; 224 < S <= 288 defaults to the mma.sync
     kernel.  Keys [lo, hi) carry logits ~70 nats above the rest, so the two ranges' reference exponents differ by ~100
     octaves in either direction (one side's weight underflows to exactly 0) or the dominant keys straddle the boundary;
     the same inputs stress the online-softmax rescale of the mma.sync kernel."""

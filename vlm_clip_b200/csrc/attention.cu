@@ -45,11 +45,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 // MASKED = false: no causal / key-padding mask (vision): keys >= S are the only thing to exclude, and only the last
 // 16-key group can contain them - the per-key mask loads and selects disappear from every other group.
-// WIDE = true: one CTA of up to 18 warps covers ALL query blocks of a (batch, head) unit (S <= 288), so K and V are staged
-// once per unit instead of once per group of 8 query blocks (ViT-L/14: 3 x less staging traffic, 17 instead of 12
-// resident warps per SM); the register cap is then 113 per thread.
-template <bool MASKED, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? 576 : 256, WIDE ? 1 : 2)
+constexpr int QK_GROUP = 4;  // 8-key tiles of S whose mma.sync chains are interleaved
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256, 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                      const uint8_t* __restrict__ key_mask, int S, int H, int causal, float scale_log2e, int Spad,
                      int q_begin) {
@@ -124,18 +123,26 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   for (int k0 = 0; k0 < kmax16; k0 += 64) {
     const int n16 = min(4, (kmax16 - k0) >> 4);  // 16-key groups in this block (warp-uniform)
     float s[8][4];
+    // S = Q K^T of this block, four 8-key tiles at a time: consecutive mma.sync go to DIFFERENT accumulators (the
+    // instruction stream is kept in program order, and four back-to-back updates of one accumulator wait a full tensor
+    // pipe latency each); the order of the additions into every accumulator is unchanged
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      if ((nt >> 1) < n16) {
-        uint32_t kf[4];
-        const __nv_bfloat16* kp = sK + (k0 + nt * 8 + (lane & 7)) * KSTRIDE + (lane >> 3) * 8;
-        ldmatrix_x4(kf, kp);
-        mma_bf16_16816(s[nt], qf[0], kf[0], kf[1]);
-        mma_bf16_16816(s[nt], qf[1], kf[2], kf[3]);
-        ldmatrix_x4(kf, kp + 32);
-        mma_bf16_16816(s[nt], qf[2], kf[0], kf[1]);
-        mma_bf16_16816(s[nt], qf[3], kf[2], kf[3]);
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; g += QK_GROUP) {
+      uint32_t kf[QK_GROUP][4];
+      const __nv_bfloat16* kp = sK + (k0 + g * 8 + (lane & 7)) * KSTRIDE + (lane >> 3) * 8;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int i = 0; i < QK_GROUP; ++i)
+          if (((g + i) >> 1) < n16) ldmatrix_x4(kf[i], kp + i * 8 * KSTRIDE + half * 32);
+#pragma unroll
+        for (int i = 0; i < QK_GROUP; ++i)
+          if (((g + i) >> 1) < n16) mma_bf16_16816(s[g + i], qf[2 * half], kf[i][0], kf[i][1]);
+#pragma unroll
+        for (int i = 0; i < QK_GROUP; ++i)
+          if (((g + i) >> 1) < n16) mma_bf16_16816(s[g + i], qf[2 * half + 1], kf[i][2], kf[i][3]);
       }
     }
     // ---- mask + running max ----
@@ -241,22 +248,20 @@ namespace vlmclip {
 int attention_fwd_mma_sync_rows(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                                 float scale, int q_begin, cudaStream_t stream) {
   const int nblocks = (S - q_begin + 15) / 16;  // 16-row query blocks from q_begin on
-  static const bool wide_ok = []() {  // A/B switch: VLMCLIP_ATTN_MMA_WIDE=0 keeps groups of 8 query blocks per CTA
-    const char* e = getenv("VLMCLIP_ATTN_MMA_WIDE");
-    return !(e != nullptr && e[0] == '0');
+  static const int max_warps = []() {  // A/B switch: query blocks (= warps) per CTA
+    const char* e = getenv("VLMCLIP_ATTN_FWD_WARPS");
+    return (e != nullptr && e[0] >= '2' && e[0] <= '8') ? e[0] - '0' : 8;
   }();
-  const bool wide = wide_ok && nblocks > 8 && nblocks <= 18;
-  const int groups = wide ? 1 : (nblocks + 7) / 8;
+  const int groups = (nblocks + max_warps - 1) / max_warps;
   int qw = (nblocks + groups - 1) / groups;
   if (qw < 4) qw = 4;  // at least four warps stage K and V (warps without query rows exit after the staging)
   const int Spad = (S + 15) / 16 * 16;
   const size_t smem = (size_t)Spad * KSTRIDE * 2 * 2 + Spad;
   const bool masked = causal != 0 || key_mask != nullptr;
   using KernT = void (*)(const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*, int, int, int, float, int, int);
-  KernT kern = wide ? (masked ? (KernT)attention_fwd_kernel<true, true> : (KernT)attention_fwd_kernel<false, true>)
-                    : (masked ? (KernT)attention_fwd_kernel<true, false> : (KernT)attention_fwd_kernel<false, false>);
-  static size_t smem_set[4] = {0, 0, 0, 0};
-  const int vi = (wide ? 2 : 0) + (masked ? 1 : 0);
+  KernT kern = masked ? (KernT)attention_fwd_kernel<true> : (KernT)attention_fwd_kernel<false>;
+  static size_t smem_set[2] = {0, 0};
+  const int vi = masked ? 1 : 0;
   if (smem > smem_set[vi]) {
     VLMCLIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set[vi] = smem;

@@ -11,6 +11,8 @@
 //                             converts to an A fragment in registers, exactly like P in the forward.
 // No atomics: every output row is owned by one warp.  8 matmul-equivalents instead of the minimal 5 (Q K^T is
 // recomputed in both kernels and twice in the first) buys independence from any forward by-product.
+#include <cstdlib>
+
 #include "../../include/vlmclip.h"
 #include "common.cuh"
 
@@ -59,30 +61,41 @@ __device__ __forceinline__ void load_a_frag(uint32_t (&f)[4][4], const __nv_bflo
   }
 }
 
-// acc[nt] (16 x 8 tile nt of a 16 x 64 block) = A (16 x 64 fragment) . rows [r0 + nt*8, +8) of a smem matrix ^T
-__device__ __forceinline__ void block_a_bt(float (&acc)[8][4], const uint32_t (&af)[4][4], const __nv_bfloat16* sB,
+// acc[nt] (16 x 8 tile nt of a 16 x 8NT block) = A (16 x 64 fragment) . rows [r0 + nt*8, +8) of a smem matrix ^T.
+// GROUP tiles at a time: consecutive mma.sync go to DIFFERENT accumulators (the instruction stream is kept in program
+// order, and four back-to-back updates of one accumulator wait a full tensor pipe latency each); the order of the
+// additions into every accumulator is unchanged.
+template <int NT, int AB_GROUP>
+__device__ __forceinline__ void block_a_bt(float (&acc)[NT][4], const uint32_t (&af)[4][4], const __nv_bfloat16* sB,
                                            int r0, int n16, int lane) {
+  constexpr int GROUP = NT < AB_GROUP ? NT : AB_GROUP;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    if ((nt >> 1) < n16) {
-      uint32_t bf[4];
-      const __nv_bfloat16* bp = sB + (r0 + nt * 8 + (lane & 7)) * KSTRIDE + (lane >> 3) * 8;
-      ldmatrix_x4(bf, bp);
-      mma_bf16_16816(acc[nt], af[0], bf[0], bf[1]);
-      mma_bf16_16816(acc[nt], af[1], bf[2], bf[3]);
-      ldmatrix_x4(bf, bp + 32);
-      mma_bf16_16816(acc[nt], af[2], bf[0], bf[1]);
-      mma_bf16_16816(acc[nt], af[3], bf[2], bf[3]);
+  for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+  for (int g = 0; g < NT; g += GROUP) {
+    uint32_t bf[GROUP][4];
+    const __nv_bfloat16* bp = sB + (r0 + g * 8 + (lane & 7)) * KSTRIDE + (lane >> 3) * 8;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (((g + i) >> 1) < n16) ldmatrix_x4(bf[i], bp + i * 8 * KSTRIDE + half * 32);
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (((g + i) >> 1) < n16) mma_bf16_16816(acc[g + i], af[2 * half], bf[i][0], bf[i][1]);
+#pragma unroll
+      for (int i = 0; i < GROUP; ++i)
+        if (((g + i) >> 1) < n16) mma_bf16_16816(acc[g + i], af[2 * half + 1], bf[i][2], bf[i][3]);
     }
   }
 }
 
-// acc (16 x 64) += T (16 x 64 block held as accumulator-layout values t[8][4]) . rows [r0, r0+64) of a smem matrix
-__device__ __forceinline__ void block_t_b(float (&acc)[8][4], const float (&t)[8][4], const __nv_bfloat16* sB, int r0,
+// acc (16 x 64) += T (16 x 8NT block held as accumulator-layout values t[NT][4]) . rows [r0, r0 + 8NT) of a smem matrix
+template <int NT>
+__device__ __forceinline__ void block_t_b(float (&acc)[8][4], const float (&t)[NT][4], const __nv_bfloat16* sB, int r0,
                                           int n16, int lane) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < NT / 2; ++kk) {
     if (kk < n16) {
       uint32_t tf[4];
       tf[0] = pack_bf16x2(t[2 * kk][0], t[2 * kk][1]);
@@ -133,8 +146,11 @@ __device__ __forceinline__ void stage_two(__nv_bfloat16* s0, __nv_bfloat16* s1, 
 }
 
 // ------------------------------------------------------------------------------------------------------ dQ
-// 144 registers: two CTAs of 7 warps per SM (154 / 194 registers left one CTA = 7 warps per SM: ncu "warps active" 10 %)
-__global__ void __maxnreg__(144)
+// MASKED = false (vision): no causal / key-padding mask.  Padding keys (>= S) only matter for the row sum of pass 1 and
+// only in the 8-key tile that straddles S: K and V rows >= S are staged as zeros, so their dS columns add nothing to dQ.
+// REGS / GROUP: register cap and mma-chain interleave (see the launcher for the numbers behind 168 / 4).
+template <bool MASKED, int REGS, int GROUP>
+__global__ void __maxnreg__(REGS)
 attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                         const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqkv,
                         const uint8_t* __restrict__ key_mask, float* __restrict__ ws_lse, float* __restrict__ ws_d, int S,
@@ -195,7 +211,7 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
   for (int k0 = 0; k0 < kmax16; k0 += 64) {
     const int n16 = min(4, (kmax16 - k0) >> 4);
     float s[8][4];
-    block_a_bt(s, qf, sK, k0, n16, lane);
+    block_a_bt<8, GROUP>(s, qf, sK, k0, n16, lane);
     float bm_a = -INFINITY, bm_b = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -203,9 +219,14 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = k0 + nt * 8 + tq * 2 + e;
-          const bool kv = sMask[key] != 0;
-          s[nt][e] = (kv && (!causal || key <= row_a)) ? s[nt][e] : -INFINITY;
-          s[nt][2 + e] = (kv && (!causal || key <= row_b)) ? s[nt][2 + e] : -INFINITY;
+          if (MASKED) {
+            const bool kv = sMask[key] != 0;
+            s[nt][e] = (kv && (!causal || key <= row_a)) ? s[nt][e] : -INFINITY;
+            s[nt][2 + e] = (kv && (!causal || key <= row_b)) ? s[nt][2 + e] : -INFINITY;
+          } else if (k0 + nt * 8 + 8 > S) {  // warp-uniform: only the tile that straddles S has padding keys
+            s[nt][e] = key < S ? s[nt][e] : -INFINITY;
+            s[nt][2 + e] = key < S ? s[nt][2 + e] : -INFINITY;
+          }
           bm_a = fmaxf(bm_a, s[nt][e]);
           bm_b = fmaxf(bm_b, s[nt][2 + e]);
         }
@@ -215,15 +236,16 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
     bm_b = quad_max(bm_b);
     const float mn_a = fmaxf(m_a, bm_a), mn_b = fmaxf(m_b, bm_b);
     const float mu_a = mn_a == -INFINITY ? 0.f : mn_a, mu_b = mn_b == -INFINITY ? 0.f : mn_b;
-    l_a *= exp2f((m_a - mu_a) * c);
-    l_b *= exp2f((m_b - mu_b) * c);
+    l_a *= fast_exp2((m_a - mu_a) * c);
+    l_b *= fast_exp2((m_b - mu_b) * c);
     m_a = mn_a;
     m_b = mn_b;
+    const float off_a = mu_a * c, off_b = mu_b * c;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       if ((nt >> 1) < n16) {
-        l_a += exp2f((s[nt][0] - mu_a) * c) + exp2f((s[nt][1] - mu_a) * c);
-        l_b += exp2f((s[nt][2] - mu_b) * c) + exp2f((s[nt][3] - mu_b) * c);
+        l_a += fast_exp2(fmaf(s[nt][0], c, -off_a)) + fast_exp2(fmaf(s[nt][1], c, -off_a));
+        l_b += fast_exp2(fmaf(s[nt][2], c, -off_b)) + fast_exp2(fmaf(s[nt][3], c, -off_b));
       }
     }
   }
@@ -248,26 +270,30 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
   float dq[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-  for (int k0 = 0; k0 < kmax16; k0 += 64) {
-    const int n16 = min(4, (kmax16 - k0) >> 4);
-    float s[8][4], dp[8][4];
-    block_a_bt(s, qf, sK, k0, n16, lane);
-    block_a_bt(dp, gf, sV, k0, n16, lane);
+  for (int k0 = 0; k0 < kmax16; k0 += 32) {  // 32 keys per block: S and dP tiles of 16 registers each
+    const int n16 = min(2, (kmax16 - k0) >> 4);
+    float s[4][4], dp[4][4];
+    block_a_bt<4, GROUP>(s, qf, sK, k0, n16, lane);
+    block_a_bt<4, GROUP>(dp, gf, sV, k0, n16, lane);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
       if ((nt >> 1) < n16) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int key = k0 + nt * 8 + tq * 2 + e;
-          const bool kv = sMask[key] != 0;
-          const float pa = (kv && (!causal || key <= row_a)) ? exp2f(fmaf(s[nt][e], c, -lse_a)) : 0.f;
-          const float pb = (kv && (!causal || key <= row_b)) ? exp2f(fmaf(s[nt][2 + e], c, -lse_b)) : 0.f;
+          float pa = fast_exp2(fmaf(s[nt][e], c, -lse_a));
+          float pb = fast_exp2(fmaf(s[nt][2 + e], c, -lse_b));
+          if (MASKED) {
+            const int key = k0 + nt * 8 + tq * 2 + e;
+            const bool kv = sMask[key] != 0;
+            pa = (kv && (!causal || key <= row_a)) ? pa : 0.f;
+            pb = (kv && (!causal || key <= row_b)) ? pb : 0.f;
+          }
           s[nt][e] = pa * (dp[nt][e] - d_a);
           s[nt][2 + e] = pb * (dp[nt][2 + e] - d_b);
         }
       }
     }
-    block_t_b(dq, s, sK, k0, n16, lane);
+    block_t_b<4>(dq, s, sK, k0, n16, lane);
   }
   __nv_bfloat16* gq = dqkv + (int64_t)b * S * ld + h * HD;
 #pragma unroll
@@ -281,7 +307,9 @@ attention_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------------------ dK, dV
-__global__ void __maxnreg__(144)
+// MASKED = false: nothing to select - padding queries carry lse = +inf (P = 0), padding key rows are never written
+template <bool MASKED, int REGS, int GROUP>
+__global__ void __maxnreg__(REGS)
 attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                          __nv_bfloat16* __restrict__ dqkv, const uint8_t* __restrict__ key_mask,
                          const float* __restrict__ ws_lse, const float* __restrict__ ws_d, int S, int H, int causal,
@@ -328,28 +356,32 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
     dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   }
   const int S16 = (S + 15) & ~15;
-  for (int i0 = causal ? j0 : 0; i0 < S16; i0 += 64) {  // causal: queries before the warp's first key see none of them
-    const int n16 = min(4, (S16 - i0) >> 4);
-    float st[8][4], dpt[8][4];  // S^T and dP^T tiles: rows = keys, columns = queries
+  for (int i0 = causal ? j0 : 0; i0 < S16; i0 += 32) {  // causal: queries before the warp's first key see none of them
+    const int n16 = min(2, (S16 - i0) >> 4);
+    float st[4][4], dpt[4][4];  // S^T and dP^T tiles: rows = keys, columns = 32 queries
     {  // the warp's K / V fragments are re-read (L1 hits) per block instead of living in 32 registers across the loop
       uint32_t kf[4][4];
       load_a_frag(kf, base + D, ld, row_a, row_b, S, tq);
-      block_a_bt(st, kf, sQ, i0, n16, lane);
+      block_a_bt<4, GROUP>(st, kf, sQ, i0, n16, lane);
     }
     {
       uint32_t vf[4][4];
       load_a_frag(vf, base + 2 * D, ld, row_a, row_b, S, tq);
-      block_a_bt(dpt, vf, sG, i0, n16, lane);
+      block_a_bt<4, GROUP>(dpt, vf, sG, i0, n16, lane);
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) {
       if ((nt >> 1) < n16) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int qi = i0 + nt * 8 + tq * 2 + e;
           const float lse = sL[qi], dd = sD[qi];
-          const float pa = (kv_a && (!causal || row_a <= qi)) ? exp2f(fmaf(st[nt][e], c, -lse)) : 0.f;
-          const float pb = (kv_b && (!causal || row_b <= qi)) ? exp2f(fmaf(st[nt][2 + e], c, -lse)) : 0.f;
+          float pa = fast_exp2(fmaf(st[nt][e], c, -lse));
+          float pb = fast_exp2(fmaf(st[nt][2 + e], c, -lse));
+          if (MASKED) {
+            pa = (kv_a && (!causal || row_a <= qi)) ? pa : 0.f;
+            pb = (kv_b && (!causal || row_b <= qi)) ? pb : 0.f;
+          }
           st[nt][e] = pa;
           st[nt][2 + e] = pb;
           dpt[nt][e] = pa * (dpt[nt][e] - dd);
@@ -357,8 +389,8 @@ attention_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloa
         }
       }
     }
-    block_t_b(dv, st, sG, i0, n16, lane);
-    block_t_b(dk, dpt, sQ, i0, n16, lane);
+    block_t_b<4>(dv, st, sG, i0, n16, lane);
+    block_t_b<4>(dk, dpt, sQ, i0, n16, lane);
   }
   __nv_bfloat16* gk = dqkv + (int64_t)b * S * ld + h * HD + D;
 #pragma unroll
@@ -387,33 +419,58 @@ int64_t attention_bwd_mma_workspace(int B, int S, int H) {
 
 int attention_bwd_mma(const void* qkv, const void* out, const void* dout, void* dqkv, const uint8_t* key_mask,
                       float* workspace, int B, int S, int H, int causal, float scale, cudaStream_t stream) {
+  // Register file: 16 384 registers per SM sub-partition.  At 168 registers per thread (no spills; the 128-register
+  // build that would allow one 13-warp CTA per ViT-B/16 head spills and measured 1 079 us against 949) three warps fit a
+  // sub-partition, twelve an SM: CTAs of 4 warps (three per SM) or 6 warps (two per SM) fill it, 5 or 7 do not.  Every
+  // CTA stages the whole head, so fewer, fuller CTAs win when both shapes waste the same share of warp slots.
+  // Measured (B200, us per call, dQ + dK/dV): S = 197, H = 12, B = 256: 949 with 4 warps, 991 with 6 (3 x 5), 1 069 with 3;
+  // S = 77 causal, H = 8: 114 / 134 / 112; S = 257, H = 16, B = 64: 626 / 491 / 705.
+  // VLMCLIP_ATTN_BWD_WARPS = 3..6 overrides the choice (A/B switch, read once).
+  static const int warps_env = []() {
+    const char* e = getenv("VLMCLIP_ATTN_BWD_WARPS");
+    return (e != nullptr && e[0] >= '3' && e[0] <= '6') ? e[0] - '0' : 0;
+  }();
   const int nblocks = (S + 15) / 16;
-  const int groups = (nblocks + 6) / 7;  // at most 7 warps per CTA: two CTAs fit the register file at 144 registers
+  int max_warps = warps_env;
+  if (max_warps == 0) {
+    double best = -1.0;
+    for (int w : {4, 6}) {  // filled share of the twelve resident warp slots; ties go to the smaller CTA
+      const int g = (nblocks + w - 1) / w, q = (nblocks + g - 1) / g;
+      const double fill = (double)nblocks / (g * q) * ((12 / q) * q / 12.0);
+      if (fill > best + 1e-9) best = fill, max_warps = w;
+    }
+  }
+  const int groups = (nblocks + max_warps - 1) / max_warps;
   const int qw = (nblocks + groups - 1) / groups;
   const int Spad = nblocks * 16;
   float* ws_lse = workspace;
   float* ws_d = workspace + (int64_t)B * H * Spad;
   const size_t smem_q = (size_t)Spad * KSTRIDE * 2 * 2 + Spad;
   const size_t smem_kv = (size_t)Spad * KSTRIDE * 2 * 2 + (size_t)Spad * 8;
-  static size_t set_q = 0, set_kv = 0;
-  if (smem_q > set_q) {
-    VLMCLIP_CUDA(cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
-    set_q = smem_q;
+  const bool masked = causal != 0 || key_mask != nullptr;
+  using DqT = void (*)(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*,
+                       float*, float*, int, int, int, float, int);
+  using DkvT = void (*)(const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, const uint8_t*, const float*,
+                        const float*, int, int, int, float, int);
+  const DqT dq_kern = masked ? attention_bwd_dq_kernel<true, 168, 4> : attention_bwd_dq_kernel<false, 168, 4>;
+  const DkvT dkv_kern = masked ? attention_bwd_dkv_kernel<true, 168, 4> : attention_bwd_dkv_kernel<false, 168, 4>;
+  static size_t set_q[2] = {0, 0}, set_kv[2] = {0, 0};
+  if (smem_q > set_q[masked]) {
+    VLMCLIP_CUDA(cudaFuncSetAttribute(dq_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    set_q[masked] = smem_q;
   }
-  if (smem_kv > set_kv) {
-    VLMCLIP_CUDA(
-        cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
-    set_kv = smem_kv;
+  if (smem_kv > set_kv[masked]) {
+    VLMCLIP_CUDA(cudaFuncSetAttribute(dkv_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+    set_kv[masked] = smem_kv;
   }
   dim3 grid(B * H, groups);
   count_launch(2);
-  attention_bwd_dq_kernel<<<grid, qw * 32, smem_q, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)out,
-                                                             (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, key_mask,
-                                                             ws_lse, ws_d, S, H, causal, scale, Spad);
+  dq_kern<<<grid, qw * 32, smem_q, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)out,
+                                             (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv, key_mask, ws_lse, ws_d, S, H,
+                                             causal, scale, Spad);
   VLMCLIP_CUDA(cudaGetLastError());
-  attention_bwd_dkv_kernel<<<grid, qw * 32, smem_kv, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout,
-                                                               (__nv_bfloat16*)dqkv, key_mask, ws_lse, ws_d, S, H, causal,
-                                                               scale, Spad);
+  dkv_kern<<<grid, qw * 32, smem_kv, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dqkv,
+                                               key_mask, ws_lse, ws_d, S, H, causal, scale, Spad);
   return report_cuda(cudaGetLastError(), "attention_bwd_mma launch");
 }
 

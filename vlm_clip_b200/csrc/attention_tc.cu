@@ -2,7 +2,7 @@
 //   HF modeling_clip.py:261-279 (eager_attention_forward), :318-331 (dispatch), :546-551 (causal + padding mask)
 // Dispatches between the tcgen05 ping-pong kernel (attention_pp.cu; S <= 224, the vision tower), its two-launch
 // key-range split (288 < S <= 384 without a mask, needs the caller's workspace) and the mma.sync kernel (attention.cu;
-// short causal / masked text sequences, ViT-L/14's S = 257 in one wide CTA per head, and everything else).
+// short causal / masked text sequences, ViT-L/14's S = 257, and everything else).
 #include <cstdio>
 #include <cstdlib>
 
@@ -22,7 +22,7 @@ int attention_fwd_pingpong_split(const void* qkv, void* out, float* workspace, i
 
 using namespace vlmclip;
 
-// VLMCLIP_ATTN_SPLIT: unset = auto (224 < S <= 288 on the wide mma.sync kernel, which measures 894 us against the
+// VLMCLIP_ATTN_SPLIT: unset = auto (224 < S <= 288 on the mma.sync kernel, which measures 890 us against the
 // split's 918 us at ViT-L/14, B=512; 288 < S <= 384 on split variant 3), 0 keeps every S > 224 on the mma.sync kernel,
 // 1 / 2 / 3 / 4 force that variant of the key-range split (attention_pp.cu: attention_fwd_pingpong_split) for all
 // 224 < S <= 384; A/B switch, read once
@@ -52,7 +52,7 @@ extern "C" int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_
   VLMCLIP_CHECK_ARG((uintptr_t)qkv % 16 == 0 && (uintptr_t)out % 16 == 0, "attention: pointers must be 16-byte aligned");
   VLMCLIP_CHECK_ARG((uintptr_t)workspace % 8 == 0, "attention: workspace must be 8-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  // Dispatch.  S > 224 exceeds the two-S-buffer TMEM map of the tcgen05 kernel: up to S = 288 (ViT-L/14) the wide
+  // Dispatch.  S > 224 exceeds the two-S-buffer TMEM map of the tcgen05 kernel: up to S = 288 (ViT-L/14) the
   // mma.sync kernel is the faster of the two measured options, beyond that it runs as two key ranges merged in the second
   // launch's epilogue (needs the workspace).  For the short causal
   // text sequences (S = 77: 60 % of a 128-row tile would be padding, every chunk takes the masked path) the mma.sync
