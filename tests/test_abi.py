@@ -61,6 +61,28 @@ def test_abi_version_and_error_channel(lib):
     assert lib.vlmclip_clip_loss_workspace(256, 512) == 4 * 256 + 256 * 256 + 2 * 256 * 512
 
 
+def test_size_queries_and_argument_checks_without_gpu(lib):
+    """Workspace / counter size queries are pure host arithmetic and the argument checks run before any CUDA call:
+    both pin the dispatch rules (which sequence lengths take the key-range split) without a device."""
+    import os
+
+    if os.environ.get("VLMCLIP_ATTN_SPLIT") is None:  # auto: S <= 224 one tcgen05 launch, <= 288 mma.sync, <= 384 split
+        assert lib.vlmclip_attention_fwd_workspace(4, 197, 12) == 0
+        assert lib.vlmclip_attention_fwd_workspace(4, 257, 16) == 0
+        assert lib.vlmclip_attention_fwd_workspace(4, 300, 16) == 2 * 4 * 300 * 16
+        assert lib.vlmclip_attention_fwd_workspace(4, 385, 16) == 0
+    assert lib.vlmclip_attention_fwd_workspace(0, 257, 16) == 0
+    assert lib.vlmclip_clip_loss_counters(512) == 21 * 4 + 4  # 21 counters per 128-row block + 4
+    rc = lib.vlmclip_attention_fwd(None, None, None, 2, 77, 8, 1, 0.125, None)
+    assert rc < 0 and b"null" in lib.vlmclip_last_error()
+    buf = ctypes.create_string_buffer(64)  # a non-null, 16-byte aligned host address: rejected by the S limit first
+    addr = (ctypes.addressof(buf) + 15) & ~15
+    rc = lib.vlmclip_attention_fwd(addr, addr, None, 2, 513, 8, 0, 0.125, None)
+    assert rc < 0 and b"512" in lib.vlmclip_last_error()
+    rc = lib.vlmclip_attention_fwd(addr + 2, addr, None, 2, 77, 8, 0, 0.125, None)
+    assert rc < 0 and b"aligned" in lib.vlmclip_last_error()
+
+
 def test_library_is_sm100a_tcgen05(lib):
     """The shipped cubin must contain the Blackwell tensor-core / TMA / TMEM instructions (cuobjdump mnemonics of
     B200_PROFILING.md), i.e. nothing silently fell back to a legacy path."""
