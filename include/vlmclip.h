@@ -158,9 +158,10 @@ int vlmclip_text_embed(const int64_t* ids, const void* tok, int tok_bf16, const 
 int vlmclip_attention_fwd(const void* qkv, void* out, const uint8_t* key_mask, int B, int S, int H, int causal,
                           float scale, void* stream);
 /* Same operator with a caller-provided scratch buffer of vlmclip_attention_fwd_workspace(B, S, H) floats (0 = none
- * needed).  With it, unmasked sequences of 225..384 tokens (ViT-L/14: S = 257) run on the tcgen05 kernel as two key
- * ranges whose partial softmaxes are merged on the device (reference exponent and row sum per row and head live in
- * the workspace between the two launches); workspace = NULL behaves exactly like vlmclip_attention_fwd. */
+ * needed).  With it, unmasked sequences of 289..384 tokens (225..384 with VLMCLIP_ATTN_SPLIT=1..4; ViT-L/14's S = 257
+ * defaults to the mma.sync kernel, which measures faster there) run on the tcgen05 kernel as two key ranges whose
+ * partial softmaxes are merged on the device (reference exponent and row sum per row and head live in the workspace
+ * between the two launches); workspace = NULL behaves exactly like vlmclip_attention_fwd. */
 int64_t vlmclip_attention_fwd_workspace(int B, int S, int H);
 int vlmclip_attention_fwd_ws(const void* qkv, void* out, const uint8_t* key_mask, float* workspace, int B, int S,
                              int H, int causal, float scale, void* stream);
